@@ -1,0 +1,17 @@
+/* Mini-GSL shim -- ORACLE / TEST INFRASTRUCTURE ONLY (never linked into the product).
+ * GSL is an un-vendored, unpinned dependency of the reference (CMakeLists.txt:9,
+ * src/Makefile:5) and is absent from this image; this header declares exactly the
+ * symbols src/redTime.cc and src/AU_cosmological_parameters.h use so that the
+ * UNMODIFIED reference sources compile.  Algorithms restated in ../gsl_shim.cc. */
+#ifndef SHIM_GSL_SF_GAMMA_H
+#define SHIM_GSL_SF_GAMMA_H
+#include "gsl_sf_result.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* ln|Gamma(zr + i zi)| and arg Gamma restricted to (-pi,pi]; redTime.cc:310-313 */
+int gsl_sf_lngamma_complex_e(double zr, double zi, gsl_sf_result *lnr, gsl_sf_result *arg);
+#ifdef __cplusplus
+}
+#endif
+#endif
