@@ -1,0 +1,167 @@
+/* redtime_b200 -- C-ABI of the B200-native Time-RG hot path.
+ *
+ * Drop-in boundary for michaelbuehlmann/redTime (reference paths below are relative to
+ * the reference repository).  The reference has no plugin API; its seams are
+ *   (i)  the executable's file/stdout contract            src/redTime.cc:1551-1745
+ *   (ii) the GSL callback `derivatives(eta,y,dy,params)`  src/redTime.cc:1416,1596
+ * and one level below: compute_Aacdbef_Rlabc_PTjm_PMRn_full (src/redTime.cc:740-744),
+ * C.D_dD (src/AU_cosmological_parameters.h:733), C.Beta_P (:632).
+ * This header exposes those seams, batched over cosmologies, with plain pointers and
+ * sizes only.  All functions return 0 on success, a negative RTRG_E* code otherwise;
+ * nothing aborts or throws across the boundary.  A handle is thread-confined.  The
+ * caller owns every host buffer; the library copies.  There is NO CPU fallback: every
+ * compute entry point fails with RTRG_ENOGPU when no CUDA device is usable.
+ */
+#ifndef REDTIME_B200_H
+#define REDTIME_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTRG_OK 0
+#define RTRG_EINVAL (-1)   /* bad argument / malformed input                       */
+#define RTRG_ENOGPU (-2)   /* no usable CUDA device (there is no CPU path)           */
+#define RTRG_ECUDA (-3)    /* CUDA runtime error, see rtrg_last_error()             */
+#define RTRG_ERANGE (-4)   /* look-up outside the reference's abort() bounds         */
+#define RTRG_EODE (-5)     /* integrator failed for at least one cosmology           */
+#define RTRG_ENOMEM (-6)
+
+#define RTRG_MAX_OUT 64    /* output redshifts per cosmology                         */
+#define RTRG_MAX_Z 200     /* interpolation redshifts (MAXTRANSFER, hdr:56)          */
+
+typedef struct rtrg_handle rtrg_handle;
+
+/* Compile-time constants of the reference turned into run-time fields, same defaults.
+ * Reference: nk/np src/redTime.cc:90-97; tolerances :141-145; z1l :1285; PRINT* :65;
+ * beta clamp src/AU_cosmological_parameters.h:537; n_lnk,a_early :664,697. */
+typedef struct rtrg_config {
+  int nk;              /* 128  (np = 4*nk)                                          */
+  double kmin, kmax;   /* 1e-3, 1  [h/Mpc]                                          */
+  double z1l;          /* 10   redshift of the cached 1-loop evaluation             */
+  double eps_abs;      /* 1e-7 RKF45 control_y_new                                  */
+  double eps_rel;      /* 1e-2                                                      */
+  double beta_kmin;    /* 1e-3 clamp of Beta_P(a,k)                                 */
+  double beta_kmax;    /* 1                                                         */
+  int n_lnk;           /* 50   growth table: n_lnk+1 wavenumbers                    */
+  int n_lna;           /* 100  growth table: n_lna+1 scale factors                  */
+  double a_early;      /* 1e-20 start of the growth integration                     */
+  int print_A, print_I, print_Q, print_bias; /* 0: optional output column groups    */
+  int device;          /* CUDA device ordinal                                       */
+  int max_attempts;    /* 100000: cap on RKF45 step attempts per cosmology          */
+  int k_shards;        /* 1; >1: this handle owns k-rows [k_rank*nk/k_shards, ...)   */
+  int k_rank;          /* 0                                                         */
+} rtrg_config;
+
+/* One cosmology = the content of params_redTime.dat plus the CAMB tables it names
+ * (src/AU_cosmological_parameters.h:231-353, :547-627, :790-832). */
+typedef struct rtrg_cosmology {
+  double params[9];      /* n_s sigma_8 h Omega_m Omega_b Omega_nu T_cmb w0 wa      */
+  int switches[4];       /* nonlinear, 1loop, print_linear, print_rsd               */
+  double z_in;
+  int n_out;
+  const double *z_out;   /* [n_out], greatest to least                              */
+  int n_T;               /* rows of the z=0 transfer file                           */
+  const double *k_T;     /* [n_T] column 0                                          */
+  const double *Tc_T;    /* [n_T] column 1 (delta_cdm/k^2)                          */
+  const double *Tb_T;    /* [n_T] column 2 (delta_b/k^2)                            */
+  int n_z;               /* interpolation redshifts (0 => Beta_P == 0)              */
+  const double *z_interp;/* [n_z] greatest to least (atof of the strings)           */
+  int n_kb;              /* rows of each interpolation file                         */
+  const double *k_b;     /* [n_kb] column 0 of the first file                       */
+  const double *Tc_b;    /* [n_z][n_kb] column 1                                    */
+  const double *Tnu_b;   /* [n_z][n_kb] column 5 (delta_massive_nu/k^2)             */
+} rtrg_cosmology;
+
+void rtrg_default_config(rtrg_config *cfg);
+const char *rtrg_last_error(void);
+const char *rtrg_version(void);
+
+/* Builds the cosmology-independent quadrature weights (FAST-PT-equivalent kernels T_n,
+ * Z kernels G_n, windows) and uploads them.  Replaces the per-call recomputation in
+ * src/redTime.cc:306-355,411-597,689-727. */
+int rtrg_create(const rtrg_config *cfg, rtrg_handle **out);
+int rtrg_destroy(rtrg_handle *h);
+/* Launch on a caller-provided CUDA stream (cudaStream_t passed as void*); NULL = own. */
+int rtrg_set_stream(rtrg_handle *h, void *cuda_stream);
+
+int rtrg_clear_cosmologies(rtrg_handle *h);
+int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *c);
+int rtrg_num_cosmologies(const rtrg_handle *h);
+/* columns of the table of cosmology i (src/redTime.cc:1670-1737): 17 by default */
+int rtrg_num_columns(const rtrg_handle *h, int icosmo);
+
+/* Host->device upload of all added cosmologies, then on the device: Beta_P tables,
+ * growth tables (RK8PD), sigma_8 normalisation and sigma_v^2 (QAG-61), initial
+ * conditions, 1-loop cache.  Replaces src/redTime.cc:1559-1586 +
+ * src/AU_cosmological_parameters.h:513-971 first-call initialisations. */
+int rtrg_prepare(rtrg_handle *h);
+
+/* The whole job (src/redTime.cc:1588-1742): evolve every cosmology with the
+ * device-resident RKF45 stepper and write the output tables.
+ *   out   : concatenated per cosmology, [n_out][nk][ncols] each (row-major)
+ *   hdr   : [n_cosmo][RTRG_MAX_OUT][5] = eta, a, z, H, sigma_v^2 per output
+ *   hdr0  : [n_cosmo][2] = eta_fin, sigmaV2(z=0)
+ *   status: [n_cosmo] 0 = ok (may be NULL)                                          */
+int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *hdr0,
+             int *status);
+/* Work counters of the last rtrg_run for cosmology i:
+ * counters[0]=RKF45 attempts, [1]=rejected, [2]=RHS evaluations, [3]=integral evaluations */
+int rtrg_counters(const rtrg_handle *h, int icosmo, long long counters[4]);
+/* number of kernel launches issued by this handle so far */
+long long rtrg_launch_count(const rtrg_handle *h);
+
+/* ---- stage-level hooks with the reference's array layouts (parity tests) ---------- */
+/* src/redTime.cc:772-778: y[0..3nk) -> P[3][np] extrapolated and windowed            */
+int rtrg_extrap_P(rtrg_handle *h, int icosmo, const double *lnP3nk, double *P3np);
+/* src/redTime.cc:740-1282: A[64*nk], R[24*nk], PTjm[9*nk], PMRn[8*nk]                */
+int rtrg_integrals_full(rtrg_handle *h, int icosmo, const double *lnP3nk, double *A64,
+                        double *R24, double *PTjm9, double *PMRn8);
+/* raw bilinear quadratures J[63][nk], PZ[63][nk], Jn0[63][nk] at the nk output rows
+ * (src/redTime.cc:781-811; index 9n+3ab+cd) and J[0][nloMR]                          */
+int rtrg_integrals_raw(rtrg_handle *h, int icosmo, const double *lnP3nk, double *J63,
+                       double *PZ63, double *Jn063, double *Jlo);
+/* src/redTime.cc:1416-1547: the Time-RG right-hand side, y,dy of length 41*nk        */
+int rtrg_derivatives(rtrg_handle *h, int icosmo, double eta, const double *y, double *dy);
+/* src/AU_cosmological_parameters.h:639-738 and :513-637                              */
+int rtrg_D_dD(rtrg_handle *h, int icosmo, double z, const double *k, int n, double *D,
+              double *dDda);
+int rtrg_Beta_P(rtrg_handle *h, int icosmo, double a, const double *k, int n, double *beta);
+/* src/AU_cosmological_parameters.h:834-930: which = 0 Plin, 1 Plin_cb, 2 Plin_nu     */
+int rtrg_Plin(rtrg_handle *h, int icosmo, int which, double z, const double *k, int n,
+              double *P);
+/* initial state y[41*nk] (src/redTime.cc:1570-1586) and scalars
+ * scal[0]=sigma8 Norm, [1]=sigmaV2(z=0) (src/AU_cosmological_parameters.h:874,961)   */
+int rtrg_initial_state(rtrg_handle *h, int icosmo, double *y, double scal[2]);
+
+/* ---- cosmology-independent tables (host side, usable without a GPU) ---------------- */
+/* grid: out[0]=np, [1]=nshift, [2]=jlo, [3]=nsup, [4]=nloMR */
+int rtrg_grid_info(int nk, double kmin, double kmax, int out[5], double *dlnk,
+                   double *lnk_pad_min);
+/* T_n (n<14): np*np doubles, row-major [u][v]; kfac: np doubles */
+int rtrg_table_T(int nk, double kmin, double kmax, int n, double *T, double *kfac);
+/* G_n (n<7): 2*np-1 doubles, G[d+np-1] */
+int rtrg_table_G(int nk, double kmin, double kmax, int n, double *G);
+/* windows WP[np], WC[np] */
+int rtrg_table_windows(int nk, double kmin, double kmax, double *WP, double *WC);
+/* assembly terms: returns count; arrays may be NULL to query the count */
+int rtrg_assembly_terms(int *row, int *src, int *index, int *kpow, double *coef, int cap);
+
+/* ---- host-side I/O mirroring the reference executable ------------------------------ */
+typedef struct rtrg_run_inputs rtrg_run_inputs;
+/* parse <dir>/params_redTime.dat and the CAMB files it names (hdr:231-353,547-627,790-832);
+ * camb_modern != 0 selects the 13-column layout (hdr:76-80) */
+int rtrg_read_run_dir(const char *dir, int camb_modern, rtrg_run_inputs **out);
+const rtrg_cosmology *rtrg_inputs_cosmology(const rtrg_run_inputs *in);
+void rtrg_free_run_inputs(rtrg_run_inputs *in);
+/* print one cosmology's result exactly as the reference's main() does (stdout format of
+ * src/redTime.cc:1602-1603,1639-1641,1670-1741; banner line of hdr:236) */
+int rtrg_print_result(void *cfile, const char *paramfile_name, int nk, int ncols, int n_out,
+                      const double *out, const double *hdr, const double *hdr0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDTIME_B200_H */

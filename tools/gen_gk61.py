@@ -20,7 +20,7 @@ weights; wg[0..14] the weights of the 30-point Gauss rule for xgk[1],xgk[3],...
 Checks performed before writing: sum of weights == 2, exactness on x^90,
 interlacing, and the three spot values recorded in SURVEY.md section 9 (V5).
 
-Usage: python gen_gk61.py > ../gsl_shim/gk61_table.h
+Usage: python tools/gen_gk61.py > oracle/gsl_shim/gk61_table.h   (and redtime_b200/csrc/gk61_table.h)
 """
 import sys
 import mpmath as mp
@@ -133,7 +133,7 @@ def main():
     assert abs(wgk[30] - mp.mpf("0.05149472942945157")) < 1e-16
 
     out = sys.stdout
-    out.write("/* GENERATED by oracle/tools/gen_gk61.py (mpmath, 80 digits) -- do not edit.\n"
+    out.write("/* GENERATED by tools/gen_gk61.py (mpmath, 80 digits) -- do not edit.\n"
               " * 61-point Gauss-Kronrod rule in QUADPACK qk61 layout. */\n")
     def arr(name, vals):
         out.write("static const double %s[%d] = {\n" % (name, len(vals)))
