@@ -1,0 +1,327 @@
+"""ctypes binding of include/redtime_b200.h (plumbing only)."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_OUT = 64
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+ERRORS = {-1: "EINVAL", -2: "ENOGPU", -3: "ECUDA", -4: "ERANGE", -5: "EODE", -6: "ENOMEM"}
+
+
+class RtrgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rtrg error %s (%d): %s" % (ERRORS.get(code, "?"), code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    """Mirror of rtrg_config (same field order)."""
+    _fields_ = [("nk", C.c_int), ("kmin", C.c_double), ("kmax", C.c_double), ("z1l", C.c_double),
+                ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("beta_kmin", C.c_double),
+                ("beta_kmax", C.c_double), ("n_lnk", C.c_int), ("n_lna", C.c_int),
+                ("a_early", C.c_double), ("print_A", C.c_int), ("print_I", C.c_int),
+                ("print_Q", C.c_int), ("print_bias", C.c_int), ("device", C.c_int),
+                ("max_attempts", C.c_int), ("k_shards", C.c_int), ("k_rank", C.c_int)]
+
+
+class _Cosmology(C.Structure):
+    _fields_ = [("params", C.c_double * 9), ("switches", C.c_int * 4), ("z_in", C.c_double),
+                ("n_out", C.c_int), ("z_out", _dp), ("n_T", C.c_int), ("k_T", _dp), ("Tc_T", _dp),
+                ("Tb_T", _dp), ("n_z", C.c_int), ("z_interp", _dp), ("n_kb", C.c_int), ("k_b", _dp),
+                ("Tc_b", _dp), ("Tnu_b", _dp)]
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(_HERE, "libredtime_b200.so")
+
+
+def load_library():
+    """Load the in-tree shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RtrgError(-2, "%s not found: build it with `make -C redtime_b200/csrc` "
+                            "(or __graft_entry__.build()); there is no Python/CPU fallback" % path)
+    lib = C.CDLL(path)
+    lib.rtrg_last_error.restype = C.c_char_p
+    lib.rtrg_version.restype = C.c_char_p
+    lib.rtrg_launch_count.restype = C.c_longlong
+    lib.rtrg_launch_count.argtypes = [C.c_void_p]
+    lib.rtrg_default_config.argtypes = [C.POINTER(Config)]
+    lib.rtrg_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.rtrg_destroy.argtypes = [C.c_void_p]
+    lib.rtrg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rtrg_clear_cosmologies.argtypes = [C.c_void_p]
+    lib.rtrg_add_cosmology.argtypes = [C.c_void_p, C.POINTER(_Cosmology)]
+    lib.rtrg_num_cosmologies.argtypes = [C.c_void_p]
+    lib.rtrg_num_columns.argtypes = [C.c_void_p, C.c_int]
+    lib.rtrg_prepare.argtypes = [C.c_void_p]
+    lib.rtrg_run.argtypes = [C.c_void_p, _dp, C.c_size_t, _dp, _dp, _ip]
+    lib.rtrg_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+    lib.rtrg_extrap_P.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    lib.rtrg_integrals_full.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    lib.rtrg_integrals_raw.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    lib.rtrg_derivatives.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _dp]
+    lib.rtrg_D_dD.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp]
+    lib.rtrg_Beta_P.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, _dp]
+    lib.rtrg_Plin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp]
+    lib.rtrg_initial_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    lib.rtrg_grid_info.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int * 5, _dp, _dp]
+    lib.rtrg_table_T.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp]
+    lib.rtrg_table_G.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp]
+    lib.rtrg_table_windows.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp]
+    lib.rtrg_assembly_terms.argtypes = [_ip, _ip, _ip, _ip, _dp, C.c_int]
+    lib.rtrg_read_run_dir.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rtrg_inputs_cosmology.argtypes = [C.c_void_p]
+    lib.rtrg_inputs_cosmology.restype = C.POINTER(_Cosmology)
+    lib.rtrg_free_run_inputs.argtypes = [C.c_void_p]
+    lib.rtrg_print_result.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
+    _lib = lib
+    return lib
+
+
+def _P(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RtrgError(rc, load_library().rtrg_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---- cosmology-independent tables (host side) ------------------------------------------
+def grid_info(nk=128, kmin=1e-3, kmax=1.0):
+    lib = load_library()
+    out = (C.c_int * 5)()
+    dl, l0 = C.c_double(), C.c_double()
+    _check(lib.rtrg_grid_info(nk, kmin, kmax, out, C.byref(dl), C.byref(l0)))
+    return dict(np=out[0], nshift=out[1], jlo=out[2], nsup=out[3], nloMR=out[4], dlnk=dl.value,
+                lnk_pad_min=l0.value)
+
+
+def table_T(n, nk=128, kmin=1e-3, kmax=1.0):
+    lib = load_library()
+    npad = 4 * nk
+    T, kf = np.zeros((npad, npad)), np.zeros(npad)
+    _check(lib.rtrg_table_T(nk, kmin, kmax, n, _P(T), _P(kf)))
+    return T, kf
+
+
+def table_G(n, nk=128, kmin=1e-3, kmax=1.0):
+    lib = load_library()
+    G = np.zeros(8 * nk - 1)
+    _check(lib.rtrg_table_G(nk, kmin, kmax, n, _P(G)))
+    return G
+
+
+def table_windows(nk=128, kmin=1e-3, kmax=1.0):
+    lib = load_library()
+    WP, WC = np.zeros(4 * nk), np.zeros(4 * nk)
+    _check(lib.rtrg_table_windows(nk, kmin, kmax, _P(WP), _P(WC)))
+    return WP, WC
+
+
+def assembly_terms():
+    lib = load_library()
+    n = lib.rtrg_assembly_terms(None, None, None, None, None, 0)
+    row, src, idx, kpw = (np.zeros(n, np.int32) for _ in range(4))
+    cf = np.zeros(n)
+    lib.rtrg_assembly_terms(row.ctypes.data_as(_ip), src.ctypes.data_as(_ip), idx.ctypes.data_as(_ip),
+                            kpw.ctypes.data_as(_ip), _P(cf), n)
+    return row, src, idx, kpw, cf
+
+
+# ---- run-directory reader (mirrors the reference's params/CAMB parsing) -----------------
+def read_run_dir(path, camb_modern=False):
+    """Parse <path>/params_redTime.dat + CAMB files through the library's C++ reader and
+    return a plain dict of numpy arrays (the argument of RedTimeB200.add_cosmology)."""
+    lib = load_library()
+    hnd = C.c_void_p()
+    rc = lib.rtrg_read_run_dir(os.fsencode(path), int(camb_modern), C.byref(hnd))
+    if rc != 0:
+        raise RtrgError(rc, "cannot read run directory %s" % path)
+    try:
+        c = lib.rtrg_inputs_cosmology(hnd).contents
+        def arr(p, n):
+            return np.ctypeslib.as_array(p, shape=(n,)).copy() if n > 0 else np.zeros(0)
+        d = dict(params=np.array(list(c.params)), switches=[int(x) for x in c.switches], z_in=c.z_in,
+                 z_out=arr(c.z_out, c.n_out), k_T=arr(c.k_T, c.n_T), Tc_T=arr(c.Tc_T, c.n_T),
+                 Tb_T=arr(c.Tb_T, c.n_T), z_interp=arr(c.z_interp, c.n_z), k_b=arr(c.k_b, c.n_kb),
+                 Tc_b=arr(c.Tc_b, c.n_z * c.n_kb).reshape(c.n_z, max(c.n_kb, 1)) if c.n_z else np.zeros((0, 0)),
+                 Tnu_b=arr(c.Tnu_b, c.n_z * c.n_kb).reshape(c.n_z, max(c.n_kb, 1)) if c.n_z else np.zeros((0, 0)))
+    finally:
+        lib.rtrg_free_run_inputs(hnd)
+    return d
+
+
+def print_result(path, nk, out, hdr, hdr0, paramfile="params_redTime.dat"):
+    """Write one cosmology's tables in the reference's stdout format to `path`."""
+    lib = load_library()
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    f = libc.fopen(os.fsencode(path), b"w")
+    if not f:
+        raise OSError("cannot open %s" % path)
+    out = _f64(out)
+    n_out, nk_, ncols = out.shape
+    hdr, hdr0 = _f64(hdr), _f64(hdr0)
+    try:
+        _check(lib.rtrg_print_result(f, paramfile.encode() if paramfile else None, nk, ncols, n_out,
+                                     _P(out), _P(hdr), _P(hdr0)))
+    finally:
+        libc.fclose(f)
+
+
+class RedTimeB200:
+    """One handle = one GPU + one (nk,kmin,kmax) grid; cosmologies are batched."""
+
+    def __init__(self, **kw):
+        lib = load_library()
+        self.lib = lib
+        self.cfg = Config()
+        lib.rtrg_default_config(C.byref(self.cfg))
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError("unknown config field %r" % k)
+            setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        _check(lib.rtrg_create(C.byref(self.cfg), C.byref(self.h)))
+        self.nk = self.cfg.nk
+        self._keep = []
+        self._nout = []
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.lib.rtrg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib.rtrg_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def clear(self):
+        _check(self.lib.rtrg_clear_cosmologies(self.h))
+        self._keep, self._nout = [], []
+
+    def add_cosmology(self, d):
+        c = _Cosmology()
+        for i in range(9):
+            c.params[i] = float(d["params"][i])
+        for i in range(4):
+            c.switches[i] = int(d["switches"][i])
+        c.z_in = float(d["z_in"])
+        keep = {k: _f64(d[k]) for k in ("z_out", "k_T", "Tc_T", "Tb_T", "z_interp", "k_b", "Tc_b", "Tnu_b")}
+        c.n_out = keep["z_out"].size
+        c.z_out = _P(keep["z_out"])
+        c.n_T = keep["k_T"].size
+        c.k_T, c.Tc_T, c.Tb_T = _P(keep["k_T"]), _P(keep["Tc_T"]), _P(keep["Tb_T"])
+        c.n_z = keep["z_interp"].size
+        c.z_interp = _P(keep["z_interp"])
+        c.n_kb = keep["k_b"].size
+        c.k_b, c.Tc_b, c.Tnu_b = _P(keep["k_b"]), _P(keep["Tc_b"]), _P(keep["Tnu_b"])
+        _check(self.lib.rtrg_add_cosmology(self.h, C.byref(c)))
+        self._nout.append(int(c.n_out))
+        return len(self._nout) - 1
+
+    @property
+    def n_cosmo(self):
+        return self.lib.rtrg_num_cosmologies(self.h)
+
+    def num_columns(self, i=0):
+        return self.lib.rtrg_num_columns(self.h, i)
+
+    def prepare(self):
+        _check(self.lib.rtrg_prepare(self.h))
+
+    def run(self, raise_on_ode_failure=True):
+        """Returns (tables, hdr, hdr0, status): tables[i] has shape [n_out_i, nk, ncols_i]."""
+        B = self.n_cosmo
+        ncols = [self.num_columns(i) for i in range(B)]
+        sizes = [self._nout[i] * self.nk * ncols[i] for i in range(B)]
+        out = np.zeros(int(sum(sizes)))
+        hdr = np.zeros((B, MAX_OUT, 5))
+        hdr0 = np.zeros((B, 2))
+        status = np.zeros(B, np.int32)
+        rc = self.lib.rtrg_run(self.h, _P(out), out.size, _P(hdr), _P(hdr0), status.ctypes.data_as(_ip))
+        if rc != 0 and (rc != -5 or raise_on_ode_failure):
+            _check(rc)
+        tables, o = [], 0
+        for i in range(B):
+            tables.append(out[o:o + sizes[i]].reshape(self._nout[i], self.nk, ncols[i]))
+            o += sizes[i]
+        return tables, hdr, hdr0, status
+
+    def counters(self, i=0):
+        c = (C.c_longlong * 4)()
+        _check(self.lib.rtrg_counters(self.h, i, c))
+        return dict(attempts=c[0], rejected=c[1], rhs=c[2], integral_evals=c[3])
+
+    def launch_count(self):
+        return int(self.lib.rtrg_launch_count(self.h))
+
+    # ---- stage-level hooks (reference layouts) -----------------------------------------
+    def extrap_P(self, lnP, i=0):
+        lnP = _f64(lnP)
+        P = np.zeros(3 * 4 * self.nk)
+        _check(self.lib.rtrg_extrap_P(self.h, i, _P(lnP), _P(P)))
+        return P.reshape(3, 4 * self.nk)
+
+    def integrals_full(self, lnP, i=0):
+        lnP = _f64(lnP)
+        nk = self.nk
+        A, R, PT, PMR = np.zeros(64 * nk), np.zeros(24 * nk), np.zeros(9 * nk), np.zeros(8 * nk)
+        _check(self.lib.rtrg_integrals_full(self.h, i, _P(lnP), _P(A), _P(R), _P(PT), _P(PMR)))
+        return A.reshape(64, nk), R.reshape(24, nk), PT.reshape(9, nk), PMR.reshape(8, nk)
+
+    def integrals_raw(self, lnP, i=0):
+        lnP = _f64(lnP)
+        nk = self.nk
+        J, PZ, J0 = np.zeros(63 * nk), np.zeros(63 * nk), np.zeros(63 * nk)
+        jlo = C.c_double()
+        _check(self.lib.rtrg_integrals_raw(self.h, i, _P(lnP), _P(J), _P(PZ), _P(J0), C.byref(jlo)))
+        return J.reshape(63, nk), PZ.reshape(63, nk), J0.reshape(63, nk), jlo.value
+
+    def derivatives(self, eta, y, i=0):
+        y = _f64(y)
+        dy = np.zeros_like(y)
+        _check(self.lib.rtrg_derivatives(self.h, i, float(eta), _P(y), _P(dy)))
+        return dy
+
+    def D_dD(self, z, k, i=0):
+        k = _f64(k)
+        D, dD = np.zeros_like(k), np.zeros_like(k)
+        _check(self.lib.rtrg_D_dD(self.h, i, float(z), _P(k), k.size, _P(D), _P(dD)))
+        return D, dD
+
+    def Beta_P(self, a, k, i=0):
+        k = _f64(k)
+        b = np.zeros_like(k)
+        _check(self.lib.rtrg_Beta_P(self.h, i, float(a), _P(k), k.size, _P(b)))
+        return b
+
+    def Plin(self, which, z, k, i=0):
+        k = _f64(k)
+        P = np.zeros_like(k)
+        _check(self.lib.rtrg_Plin(self.h, i, int(which), float(z), _P(k), k.size, _P(P)))
+        return P
+
+    def initial_state(self, i=0):
+        y = np.zeros(41 * self.nk)
+        s = np.zeros(2)
+        _check(self.lib.rtrg_initial_state(self.h, i, _P(y), _P(s)))
+        return y, s

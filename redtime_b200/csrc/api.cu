@@ -1,0 +1,836 @@
+// C-ABI of the B200-native Time-RG hot path (see include/redtime_b200.h).
+// Host orchestration only: table upload, batch staging, kernel launch sequences.  Every
+// numerical result is produced by the CUDA kernels; there is no CPU execution path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/redtime_b200.h"
+#include "fastpt_tables.h"
+#include "rtrg_device.h"
+
+namespace rtrg {
+// kernels_integrals.cu
+int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
+                     double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
+                     cudaStream_t st);
+void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
+                        const int *mask, cudaStream_t st);
+int integrals_configure();
+// kernels_linear.cu
+int linear_upload_constants();
+int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st);
+void launch_hook_DdD(const Batch &S, int b, double z, const double *k, int n, double *D, double *dD,
+                     int *err, cudaStream_t st);
+void launch_hook_beta(const Batch &S, int b, double a, const double *k, int n, double *beta, int *err,
+                      cudaStream_t st);
+void launch_hook_plin(const Batch &S, int b, int which, double z, const double *k, int n, double *P,
+                      cudaStream_t st);
+// kernels_ode.cu
+void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *dyv, int stage,
+                const int *mask, cudaStream_t st);
+void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st);
+void launch_final(const Batch &S, const int *mask, cudaStream_t st);
+void launch_ctrl_begin(const Batch &S, cudaStream_t st);
+void launch_ctrl_end(const Batch &S, int max_attempts, cudaStream_t st);
+void launch_accept(const Batch &S, cudaStream_t st);
+void launch_output(const Batch &S, const double *kgrid, cudaStream_t st);
+}  // namespace rtrg
+
+using namespace rtrg;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(RTRG_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+struct HostCosmo {
+  Cosmo c;
+  std::vector<double> z_out, lnkT, lnT, anodes, kb, beta;
+};
+
+struct rtrg_handle {
+  rtrg_config cfg;
+  GridSpec grid;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  IntegralTabs tb;
+  std::vector<void *> table_allocs, batch_allocs;
+  double *d_kgrid = nullptr;
+  std::vector<double> kgrid;
+  std::vector<HostCosmo> cos;
+  Batch S;
+  bool prepared = false;
+  long long launches = 0;
+  std::vector<long long> out_off, counters;
+  std::vector<int> ncols;
+  size_t out_total = 0;
+  bool any_full = false, any_1loop = false, any_pr = false;
+  double *d_yinit = nullptr, *d_raw = nullptr, *d_scratch = nullptr;
+  int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
+  size_t scratch_len = 0;
+};
+
+template <class T>
+static int dev_alloc(std::vector<void *> &pool, T **p, size_t n, bool zero = true) {
+  void *q = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+  if (zero) cudaMemset(q, 0, n * sizeof(T));
+  pool.push_back(q);
+  *p = (T *)q;
+  return RTRG_OK;
+}
+template <class T>
+static int dev_upload(std::vector<void *> &pool, const T **p, const std::vector<T> &v) {
+  T *q = nullptr;
+  int rc = dev_alloc(pool, &q, v.size(), false);
+  if (rc) return rc;
+  if (!v.empty()) {
+    cudaError_t e = cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(RTRG_ECUDA, "cudaMemcpy H2D: %s", cudaGetErrorString(e));
+  }
+  *p = q;
+  return RTRG_OK;
+}
+static void free_pool(std::vector<void *> &pool) {
+  for (void *p : pool) cudaFree(p);
+  pool.clear();
+}
+
+static int num_columns(const rtrg_config &cfg, const Cosmo &c) {
+  // rt:1670-1737
+  int n = 1 + 3;
+  if (c.sw_pl) n += 6;
+  if (cfg.print_A) n += 14;
+  if (cfg.print_I) n += 14;
+  if (c.sw_pr) n += cfg.print_bias ? (5 + 9 + 8) : 7;
+  if (cfg.print_Q) n += 24;
+  return n;
+}
+
+extern "C" {
+
+void rtrg_default_config(rtrg_config *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->nk = 128;
+  cfg->kmin = 1e-3;
+  cfg->kmax = 1.0;
+  cfg->z1l = 10.0;
+  cfg->eps_abs = 1e-7;
+  cfg->eps_rel = 1e-2;
+  cfg->beta_kmin = 1e-3;
+  cfg->beta_kmax = 1.0;
+  cfg->n_lnk = 50;
+  cfg->n_lna = 100;
+  cfg->a_early = 1e-20;
+  cfg->device = 0;
+  cfg->max_attempts = 100000;
+  cfg->k_shards = 1;
+  cfg->k_rank = 0;
+}
+
+const char *rtrg_last_error(void) { return g_err.c_str(); }
+const char *rtrg_version(void) { return "redtime_b200 0.1 (sm_100a)"; }
+
+int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
+  if (!cfg || !out) return fail(RTRG_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->nk < 16 || cfg->nk % 16 || !(cfg->kmin > 0) || !(cfg->kmax > cfg->kmin) || cfg->n_lnk < 3 ||
+      cfg->n_lna < 3 || cfg->k_shards < 1 || cfg->k_rank < 0 || cfg->k_rank >= cfg->k_shards ||
+      (cfg->nk / BIL_R) % cfg->k_shards)
+    return fail(RTRG_EINVAL, "invalid configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(RTRG_ENOGPU, "no CUDA device available; redtime_b200 has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(RTRG_EINVAL, "device %d out of range", cfg->device);
+  CU(cudaSetDevice(cfg->device));
+  rtrg_handle *h = new rtrg_handle();
+  h->cfg = *cfg;
+  h->grid = make_grid(cfg->nk, cfg->kmin, cfg->kmax);
+  std::memset(&h->S, 0, sizeof h->S);
+  std::memset(&h->tb, 0, sizeof h->tb);
+  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  if (linear_upload_constants() != 0) {
+    delete h;
+    return fail(RTRG_ECUDA, "constant upload failed");
+  }
+  integrals_configure();
+
+  const GridSpec &g = h->grid;
+  const int nk = g.nk, np = g.np;
+  IntegralTabs &tb = h->tb;
+  tb.nk = nk;
+  tb.np = np;
+  tb.nshift = g.nshift;
+  tb.jlo = g.jlo;
+  tb.nsup = g.nsup;
+  tb.nloMR = g.nloMR;
+  tb.NV = g.nsup + BIL_R - 1;
+  tb.NVp = (tb.NV + BIL_R - 1) / BIL_R * BIL_R;
+  tb.LP = tb.NVp + BIL_R;
+  tb.NUp = nk - BIL_R + tb.NVp;
+  tb.ldT = (nk + g.nsup - 1 + 7) / 8 * 8;
+  tb.nchunk = (tb.NV + 352 - 1) / 352;
+  tb.dlnk = g.dlnk;
+
+  // --- circulant kernels, built in parallel on the host, packed into the compact layout
+  const int UMIN = g.nshift - (np - 1), NU = nk + g.nsup - 1;
+  std::vector<double> Tc((size_t)N_JKERN * tb.NUp * tb.ldT, 0.0), kfac((size_t)N_JKERN * nk);
+  std::vector<double> Tlo((size_t)g.nsup * g.nsup);
+  double kfac_lo = 0;
+  {
+    std::vector<std::thread> th;
+    for (int n = 0; n < N_JKERN; n++)
+      th.emplace_back([&, n]() {
+        std::vector<double> T, kf;
+        build_T(g, n, T, kf);
+        double *dst = &Tc[(size_t)n * tb.NUp * tb.ldT];
+        for (int vv = 0; vv < NU; vv++) {
+          const int v = ((vv + UMIN) % np + np) % np;
+          for (int uu = 0; uu < NU; uu++) {
+            const int u = ((uu + UMIN) % np + np) % np;
+            dst[(size_t)vv * tb.ldT + uu] = T[(size_t)u * np + v];
+          }
+        }
+        for (int i = 0; i < nk; i++) kfac[(size_t)n * nk + i] = kf[g.nshift + i];
+        if (n == 0) {
+          kfac_lo = kf[g.nloMR];
+          for (int ll = 0; ll < g.nsup; ll++) {
+            const int v = ((g.nloMR - (np - 1 - ll)) % np + np) % np;
+            for (int jj = 0; jj < g.nsup; jj++) {
+              const int u = ((g.nloMR - (np - 1 - jj)) % np + np) % np;
+              Tlo[(size_t)ll * g.nsup + jj] = T[(size_t)u * np + v];
+            }
+          }
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  tb.kfac_lo = kfac_lo;
+  std::vector<double> G((size_t)N_ZKERN * (2 * np - 1));
+  for (int n = 0; n < N_ZKERN; n++) {
+    std::vector<double> Gn;
+    build_G(g, n, Gn);
+    std::copy(Gn.begin(), Gn.end(), G.begin() + (size_t)n * (2 * np - 1));
+  }
+  std::vector<double> WP(np), kpad(np);
+  h->kgrid.resize(nk);
+  std::vector<double> lnkArr(nk);
+  const double lnkmin = std::log(cfg->kmin);
+  for (int i = 0; i < nk; i++) {  // rt:1559-1562
+    lnkArr[i] = lnkmin + g.dlnk * i;
+    h->kgrid[i] = std::exp(lnkArr[i]);
+  }
+  // --- Pab stencil for every padded sample (rt:181-232, itp:68-78)
+  std::vector<int> ex_n0(np);
+  std::vector<double> ex_w((size_t)4 * np, 0.0), ex_dx(np, 0.0);
+  for (int ip = 0; ip < np; ip++) {
+    WP[ip] = window_P(g, ip);
+    const double k = std::exp(g.lnk_pad_min + g.dlnk * ip), lnk = std::log(k);
+    kpad[ip] = k;
+    const int nguess = (int)((lnk - lnkArr[0]) / g.dlnk);
+    int n = (nguess > 2 ? nguess - 2 : 0);
+    if (n > nk - 1) n = nk - 1;
+    while (n < nk - 1 && lnkArr[n + 1] < lnk) n++;
+    int type = 0;
+    if (n == 0) type = -1;
+    if (n == nk - 2) type = 1;
+    if (n >= nk - 1 || lnk > lnkArr[nk - 1]) type = 2;
+    double *w = &ex_w[(size_t)4 * ip];
+    if (type == 0) {
+      const double *p = &lnkArr[n - 1];
+      ex_n0[ip] = n - 1;
+      w[0] = (lnk - p[1]) * (lnk - p[2]) * (lnk - p[3]) / (p[0] - p[1]) / (p[0] - p[2]) / (p[0] - p[3]);
+      w[1] = (lnk - p[0]) * (lnk - p[2]) * (lnk - p[3]) / (p[1] - p[0]) / (p[1] - p[2]) / (p[1] - p[3]);
+      w[2] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[3]) / (p[2] - p[0]) / (p[2] - p[1]) / (p[2] - p[3]);
+      w[3] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[2]) / (p[3] - p[0]) / (p[3] - p[1]) / (p[3] - p[2]);
+    } else if (type == 2) {
+      ex_n0[ip] = nk - 4;
+      w[3] = 1.0;
+      ex_dx[ip] = lnk - lnkArr[nk - 1];
+    } else {
+      const int n0 = std::min(n, nk - 4);
+      ex_n0[ip] = n0;
+      const double t = (lnk - lnkArr[n]) / (lnkArr[n + 1] - lnkArr[n]);
+      w[n - n0] = 1.0 - t;
+      w[n + 1 - n0] = t;
+    }
+  }
+  // --- assembly table sorted by output row
+  std::vector<AsmTerm> terms = assembly_terms();
+  std::stable_sort(terms.begin(), terms.end(), [](const AsmTerm &a, const AsmTerm &b) { return a.row < b.row; });
+  std::vector<int> t_start(N_SRC + 1, 0);
+  std::vector<short> t_src, t_index, t_kpow;
+  std::vector<double> t_coef;
+  for (const AsmTerm &t : terms) {
+    t_start[t.row + 1]++;
+    t_src.push_back(t.src);
+    t_index.push_back(t.index);
+    t_kpow.push_back(t.kpow);
+    t_coef.push_back(t.coef);
+  }
+  for (int r = 0; r < N_SRC; r++) t_start[r + 1] += t_start[r];
+  tb.n_terms = (int)terms.size();
+
+  int rc = 0;
+  auto &P = h->table_allocs;
+  rc = rc ? rc : dev_upload(P, &tb.Tc, Tc);
+  rc = rc ? rc : dev_upload(P, &tb.Tlo, Tlo);
+  rc = rc ? rc : dev_upload(P, &tb.kfac, kfac);
+  rc = rc ? rc : dev_upload(P, &tb.G, G);
+  rc = rc ? rc : dev_upload(P, &tb.WP, WP);
+  rc = rc ? rc : dev_upload(P, &tb.kpad, kpad);
+  rc = rc ? rc : dev_upload(P, &tb.kgrid, h->kgrid);
+  rc = rc ? rc : dev_upload(P, &tb.ex_n0, ex_n0);
+  rc = rc ? rc : dev_upload(P, &tb.ex_w, ex_w);
+  rc = rc ? rc : dev_upload(P, &tb.ex_dx, ex_dx);
+  rc = rc ? rc : dev_upload(P, &tb.t_start, t_start);
+  rc = rc ? rc : dev_upload(P, &tb.t_src, t_src);
+  rc = rc ? rc : dev_upload(P, &tb.t_index, t_index);
+  rc = rc ? rc : dev_upload(P, &tb.t_kpow, t_kpow);
+  rc = rc ? rc : dev_upload(P, &tb.t_coef, t_coef);
+  if (rc) {
+    rtrg_destroy(h);
+    return rc;
+  }
+  h->d_kgrid = const_cast<double *>(tb.kgrid);
+  *out = h;
+  return RTRG_OK;
+}
+
+int rtrg_destroy(rtrg_handle *h) {
+  if (!h) return RTRG_OK;
+  cudaSetDevice(h->cfg.device);
+  free_pool(h->batch_allocs);
+  free_pool(h->table_allocs);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return RTRG_OK;
+}
+
+int rtrg_set_stream(rtrg_handle *h, void *cuda_stream) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return RTRG_OK;
+}
+
+int rtrg_clear_cosmologies(rtrg_handle *h) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  h->cos.clear();
+  h->prepared = false;
+  return RTRG_OK;
+}
+
+int rtrg_num_cosmologies(const rtrg_handle *h) { return h ? (int)h->cos.size() : 0; }
+
+int rtrg_num_columns(const rtrg_handle *h, int i) {
+  if (!h || i < 0 || i >= (int)h->cos.size()) return RTRG_EINVAL;
+  return num_columns(h->cfg, h->cos[i].c);
+}
+
+int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) {
+  if (!h || !in) return fail(RTRG_EINVAL, "null argument");
+  if (in->n_out < 1 || in->n_out > RTRG_MAX_OUT || !in->z_out) return fail(RTRG_EINVAL, "bad n_out");
+  if (in->n_T < 4 || !in->k_T || !in->Tc_T || !in->Tb_T) return fail(RTRG_EINVAL, "bad transfer table");
+  if (in->n_z < 0 || in->n_z > RTRG_MAX_Z || in->n_z == 1) return fail(RTRG_EINVAL, "bad n_z");
+  if (in->n_z > 0 && (in->n_kb < 4 || !in->z_interp || !in->k_b || !in->Tc_b || !in->Tnu_b))
+    return fail(RTRG_EINVAL, "bad interpolation tables");
+  HostCosmo hc;
+  Cosmo &c = hc.c;
+  std::memset(&c, 0, sizeof c);
+  const double *p = in->params;
+  c.ns = p[0], c.s8 = p[1], c.h = p[2], c.Om = p[3], c.Ob = p[4], c.On = p[5], c.TK = p[6], c.w0 = p[7], c.wa = p[8];
+  c.z_in = in->z_in;
+  cosmo_derive(c);
+  c.sw_nl = in->switches[0], c.sw_1l = in->switches[1], c.sw_pl = in->switches[2], c.sw_pr = in->switches[3];
+  c.n_out = in->n_out;
+  hc.z_out.assign(in->z_out, in->z_out + in->n_out);
+  // z=0 transfer function: T_cb = f_b T_b + f_c T_c, tabulated as ln(T/T[0]) vs ln k (hdr:804-823)
+  const double f_b_cb = c.Ob / (c.Om - c.On), f_c_cb = 1.0 - f_b_cb;
+  c.nT = in->n_T;
+  hc.lnkT.resize(c.nT);
+  hc.lnT.resize(c.nT);
+  double T0 = 0;
+  for (int i = 0; i < c.nT; i++) {
+    const double Ti = f_b_cb * in->Tb_T[i] + f_c_cb * in->Tc_T[i];
+    if (i == 0) T0 = Ti;
+    hc.lnkT[i] = std::log(in->k_T[i]);
+    hc.lnT[i] = std::log(Ti / T0);
+  }
+  // Beta table: f_nu T_nu / T_c on (a, k) (hdr:556-623)
+  c.n_z = in->n_z;
+  c.n_kb = in->n_z > 0 ? in->n_kb : 0;
+  const double fn = c.On / c.Om;
+  hc.anodes.resize(c.n_z);
+  for (int i = 0; i < c.n_z; i++) hc.anodes[i] = 1.0 / (1.0 + in->z_interp[i]);
+  if (c.n_z > 0) {
+    hc.kb.assign(in->k_b, in->k_b + c.n_kb);
+    hc.beta.resize((size_t)c.n_z * c.n_kb);
+    for (size_t i = 0; i < hc.beta.size(); i++) hc.beta[i] = fn * in->Tnu_b[i] / in->Tc_b[i];
+  }
+  h->cos.push_back(std::move(hc));
+  h->prepared = false;
+  return RTRG_OK;
+}
+
+int rtrg_prepare(rtrg_handle *h) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (h->cos.empty()) return fail(RTRG_EINVAL, "no cosmologies");
+  CU(cudaSetDevice(h->cfg.device));
+  free_pool(h->batch_allocs);
+  h->prepared = false;
+  const rtrg_config &cfg = h->cfg;
+  const int B = (int)h->cos.size(), nk = cfg.nk, np = 4 * nk;
+  Batch &S = h->S;
+  std::memset(&S, 0, sizeof S);
+  S.B = B, S.nk = nk, S.np = np, S.n_lna = cfg.n_lna, S.n_lnk = cfg.n_lnk;
+  S.nkk = nk + cfg.n_lnk + 1;
+  S.eps_abs = cfg.eps_abs, S.eps_rel = cfg.eps_rel, S.z1l = cfg.z1l;
+  S.beta_kmin = cfg.beta_kmin, S.beta_kmax = cfg.beta_kmax, S.a_early = cfg.a_early;
+  S.print_A = cfg.print_A, S.print_I = cfg.print_I, S.print_Q = cfg.print_Q, S.print_bias = cfg.print_bias;
+  const int rows_per = nk / cfg.k_shards;
+  S.k_lo = cfg.k_rank * rows_per;
+  S.k_hi = S.k_lo + rows_per;
+
+  // --- pools + per-cosmology scalars
+  std::vector<Cosmo> cs(B);
+  std::vector<double> lnkT, lnT, anodes, kb, beta, zout((size_t)B * MAX_OUT, 0.0), aout((size_t)B * MAX_OUT, 1.0),
+      etaout((size_t)B * MAX_OUT, 0.0);
+  h->out_off.assign(B, 0);
+  h->ncols.assign(B, 0);
+  size_t off = 0;
+  int n_zmax = 2;
+  h->any_full = h->any_1loop = h->any_pr = false;
+  for (int b = 0; b < B; b++) {
+    HostCosmo &hc = h->cos[b];
+    Cosmo c = hc.c;
+    c.offT = (long long)lnkT.size();
+    lnkT.insert(lnkT.end(), hc.lnkT.begin(), hc.lnkT.end());
+    lnT.insert(lnT.end(), hc.lnT.begin(), hc.lnT.end());
+    c.offA = (long long)anodes.size();
+    anodes.insert(anodes.end(), hc.anodes.begin(), hc.anodes.end());
+    c.offKb = (long long)kb.size();
+    kb.insert(kb.end(), hc.kb.begin(), hc.kb.end());
+    c.offB = (long long)beta.size();
+    beta.insert(beta.end(), hc.beta.begin(), hc.beta.end());
+    n_zmax = std::max(n_zmax, c.n_z);
+    for (int i = 0; i < c.n_out; i++) {  // hdr:274-277
+      const double z = hc.z_out[i], a = 1.0 / (1.0 + z);
+      zout[(size_t)b * MAX_OUT + i] = z;
+      aout[(size_t)b * MAX_OUT + i] = a;
+      etaout[(size_t)b * MAX_OUT + i] = std::log(a / c.a_in);
+    }
+    h->ncols[b] = num_columns(cfg, c);
+    h->out_off[b] = (long long)off;
+    off += (size_t)c.n_out * nk * h->ncols[b];
+    if (c.sw_nl && !c.sw_1l) h->any_full = true;
+    if (c.sw_nl && c.sw_1l) h->any_1loop = true;
+    if (c.sw_pr) h->any_pr = true;
+    cs[b] = c;
+  }
+  h->out_total = off;
+  S.n_zmax = n_zmax;
+
+  auto &P = h->batch_allocs;
+  int rc = 0;
+  {
+    const Cosmo *dc = nullptr;
+    rc = rc ? rc : dev_upload(P, &dc, cs);
+    S.cosmo = const_cast<Cosmo *>(dc);
+    const double *q = nullptr;
+    rc = rc ? rc : dev_upload(P, &q, zout), S.zout = const_cast<double *>(q);
+    rc = rc ? rc : dev_upload(P, &q, aout), S.aout = const_cast<double *>(q);
+    rc = rc ? rc : dev_upload(P, &q, etaout), S.etaout = const_cast<double *>(q);
+    rc = rc ? rc : dev_upload(P, &S.lnkT, lnkT);
+    rc = rc ? rc : dev_upload(P, &S.lnT, lnT);
+    rc = rc ? rc : dev_upload(P, &S.anodes, anodes);
+    rc = rc ? rc : dev_upload(P, &S.kb, kb);
+    rc = rc ? rc : dev_upload(P, &S.beta, beta);
+    // growth-table axes (hdr:677-687)
+    std::vector<double> lna(cfg.n_lna + 1), lnkg(cfg.n_lnk + 1);
+    const double lna_min = std::log(GROWTH_A_MIN), dlna = std::log(GROWTH_A_MAX / GROWTH_A_MIN) / cfg.n_lna;
+    const double lnk_min = std::log(GROWTH_K_MIN), dlnk = std::log(GROWTH_K_MAX / GROWTH_K_MIN) / cfg.n_lnk;
+    for (int i = 0; i <= cfg.n_lna; i++) lna[i] = lna_min + dlna * i;
+    for (int j = 0; j <= cfg.n_lnk; j++) lnkg[j] = lnk_min + dlnk * j;
+    rc = rc ? rc : dev_upload(P, &S.lna, lna);
+    rc = rc ? rc : dev_upload(P, &S.lnkg, lnkg);
+    std::vector<long long> oo(h->out_off);
+    const long long *dq = nullptr;
+    rc = rc ? rc : dev_upload(P, &dq, oo), S.out_off = const_cast<long long *>(dq);
+    const int *di = nullptr;
+    rc = rc ? rc : dev_upload(P, &di, h->ncols), S.ncols = const_cast<int *>(di);
+  }
+  const size_t NE = (size_t)B * N_U * nk, ng = (size_t)(cfg.n_lna + 1) * (cfg.n_lnk + 1);
+  const IntegralTabs &tb = h->tb;
+  rc = rc ? rc : dev_alloc(P, &S.bred, (size_t)B * n_zmax * S.nkk);
+  rc = rc ? rc : dev_alloc(P, &S.G, B * ng);
+  rc = rc ? rc : dev_alloc(P, &S.dD, B * ng);
+  rc = rc ? rc : dev_alloc(P, &S.Dnorm, (size_t)B * (cfg.n_lnk + 1));
+  rc = rc ? rc : dev_alloc(P, &S.Grow, (size_t)B * (cfg.n_lna + 1) * nk);
+  rc = rc ? rc : dev_alloc(P, &S.dDrow, (size_t)B * (cfg.n_lna + 1) * nk);
+  rc = rc ? rc : dev_alloc(P, &S.D0row, (size_t)B * nk);
+  rc = rc ? rc : dev_alloc(P, &S.Tgrid, (size_t)B * nk);
+  rc = rc ? rc : dev_alloc(P, &S.src_z1l, (size_t)B * N_SRC * nk);
+  rc = rc ? rc : dev_alloc(P, &S.D_z1l, (size_t)B * nk);
+  rc = rc ? rc : dev_alloc(P, &S.y_z1l, (size_t)B * 3 * nk);
+  rc = rc ? rc : dev_alloc(P, &S.y, NE);
+  rc = rc ? rc : dev_alloc(P, &S.ytmp, NE);
+  rc = rc ? rc : dev_alloc(P, &S.ynew, NE);
+  rc = rc ? rc : dev_alloc(P, &S.yerr, NE);
+  rc = rc ? rc : dev_alloc(P, &S.kst, RK_STAGES * NE);
+  rc = rc ? rc : dev_alloc(P, &h->d_yinit, NE);
+  rc = rc ? rc : dev_alloc(P, &S.src, (size_t)B * N_SRC * nk);
+  rc = rc ? rc : dev_alloc(P, &S.Prev, (size_t)B * 3 * tb.LP);
+  rc = rc ? rc : dev_alloc(P, &S.P3, (size_t)B * 3 * np);
+  rc = rc ? rc : dev_alloc(P, &S.Jpart, (size_t)B * N_JKERN * tb.nchunk * 9 * nk);
+  rc = rc ? rc : dev_alloc(P, &S.PZb, (size_t)B * N_ZKERN * 3 * nk);
+  rc = rc ? rc : dev_alloc(P, &S.Jlo, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.t, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.h, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.h_try, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.rmax_bits, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.i_out, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.flag_out, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.flag_step, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.flag_acc, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.final_step, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.done, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.m_full_step, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.m_full_acc, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.m_out_int, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &S.counters, (size_t)4 * B);
+  rc = rc ? rc : dev_alloc(P, &S.n_active, 1);
+  rc = rc ? rc : dev_alloc(P, &S.out, h->out_total);
+  rc = rc ? rc : dev_alloc(P, &S.hdr, (size_t)B * MAX_OUT * 5);
+  rc = rc ? rc : dev_alloc(P, &S.hdr0, (size_t)B * 2);
+  rc = rc ? rc : dev_alloc(P, &h->d_hookmask, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &h->d_minit, (size_t)B);
+  rc = rc ? rc : dev_alloc(P, &h->d_err, 1);
+  h->d_raw = nullptr;
+  h->d_scratch = nullptr;
+  h->scratch_len = 0;
+  if (rc) {
+    free_pool(P);
+    return rc;
+  }
+
+  cudaStream_t st = h->stream;
+  h->launches += launch_linear_init(S, h->d_kgrid, st);
+  CU(cudaMemcpyAsync(h->d_yinit, S.y, NE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (h->any_1loop) {
+    // 1-loop cache: the integrals of the linear spectrum at z1l (rt:1295-1313)
+    std::vector<int> m(B);
+    for (int b = 0; b < B; b++) m[b] = cs[b].sw_nl && cs[b].sw_1l;
+    CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->launches += launch_integrals(tb, S, S.y_z1l, 3LL * nk, S.src_z1l, nullptr, h->d_minit, h->any_pr,
+                                    cfg.print_bias, st);
+  }
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  // status of the device-side initialisation
+  CU(cudaMemcpy(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < B; b++) h->cos[b].c.Norm = cs[b].Norm, h->cos[b].c.sigv2_0 = cs[b].sigv2_0, h->cos[b].c.status = cs[b].status;
+  h->prepared = true;
+  return RTRG_OK;
+}
+
+int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *hdr0, int *status) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (!h->prepared) return fail(RTRG_EINVAL, "rtrg_prepare() has not been called");
+  if (out && out_len < h->out_total) return fail(RTRG_EINVAL, "output buffer too small (%zu < %zu)", out_len, h->out_total);
+  CU(cudaSetDevice(h->cfg.device));
+  Batch &S = h->S;
+  const IntegralTabs &tb = h->tb;
+  const int B = S.B, nk = S.nk;
+  const size_t NE = (size_t)B * N_U * nk;
+  cudaStream_t st = h->stream;
+
+  // --- reset the integrator state (rt:1598-1599): eta = 0, deta = 1e-2 (eta_fin - eta)
+  std::vector<double> h0(B);
+  for (int b = 0; b < B; b++) h0[b] = 1e-2 * (std::log(1.0 / h->cos[b].c.a_in) - 0.0);
+  CU(cudaMemcpyAsync(S.y, h->d_yinit, NE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemsetAsync(S.t, 0, B * sizeof(double), st));
+  CU(cudaMemcpyAsync(S.h, h0.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(S.i_out, 0, B * sizeof(int), st));
+  CU(cudaMemsetAsync(S.done, 0, B * sizeof(int), st));
+  CU(cudaMemsetAsync(S.counters, 0, 4 * B * sizeof(long long), st));
+  CU(cudaMemcpyAsync(S.n_active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
+  const int with_jlo = h->cfg.print_bias;
+
+  // --- dydt_in of the first step
+  if (h->any_full) {
+    std::vector<int> m(B);
+    for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
+    CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, h->any_pr, 0, st);
+  }
+  launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st), h->launches++;
+
+  int n_active = B;
+  long long rounds = 0;
+  const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
+  while (n_active > 0 && rounds < max_rounds) {
+    launch_ctrl_begin(S, st), h->launches++;
+    if (h->any_1loop)
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, h->any_pr, with_jlo, st);
+    launch_output(S, h->d_kgrid, st), h->launches++;
+    for (int s = 1; s < RK_STAGES; s++) {
+      launch_combine(S, s, S.flag_step, st), h->launches++;
+      if (h->any_full)
+        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, h->any_pr, 0, st);
+      launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st), h->launches++;
+    }
+    launch_final(S, S.flag_step, st), h->launches++;
+    launch_ctrl_end(S, h->cfg.max_attempts, st), h->launches++;
+    launch_accept(S, st), h->launches++;
+    if (h->any_full)
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, h->any_pr, 0, st);
+    launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st), h->launches++;
+    CU(cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    rounds++;
+  }
+  CU(cudaGetLastError());
+
+  if (out) CU(cudaMemcpyAsync(out, S.out, h->out_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (hdr) CU(cudaMemcpyAsync(hdr, S.hdr, (size_t)B * MAX_OUT * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (hdr0) CU(cudaMemcpyAsync(hdr0, S.hdr0, (size_t)B * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  h->counters.assign((size_t)4 * B, 0);
+  CU(cudaMemcpyAsync(h->counters.data(), S.counters, 4 * B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  std::vector<Cosmo> cs(B);
+  CU(cudaMemcpyAsync(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int worst = RTRG_OK;
+  for (int b = 0; b < B; b++) {
+    if (status) status[b] = cs[b].status;
+    if (cs[b].status) worst = RTRG_EODE;
+  }
+  if (n_active > 0) return fail(RTRG_EODE, "integration did not finish within %lld rounds", max_rounds);
+  if (worst) return fail(worst, "at least one cosmology failed (see status[])");
+  return RTRG_OK;
+}
+
+int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
+  if (!h || i < 0 || (size_t)(4 * i + 3) >= h->counters.size()) return RTRG_EINVAL;
+  for (int j = 0; j < 4; j++) counters[j] = h->counters[4 * i + j];
+  return RTRG_OK;
+}
+long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------- hooks
+static int hook_check(rtrg_handle *h, int icosmo) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (!h->prepared) return fail(RTRG_EINVAL, "rtrg_prepare() has not been called");
+  if (icosmo < 0 || icosmo >= h->S.B) return fail(RTRG_EINVAL, "cosmology index out of range");
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail(RTRG_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return RTRG_OK;
+}
+static int hook_mask(rtrg_handle *h, int icosmo) {
+  std::vector<int> m(h->S.B, 0);
+  m[icosmo] = 1;
+  CU(cudaMemcpyAsync(h->d_hookmask, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  return RTRG_OK;
+}
+static int scratch(rtrg_handle *h, size_t n) {
+  if (h->scratch_len >= n) return RTRG_OK;
+  double *p = nullptr;
+  int rc = dev_alloc(h->batch_allocs, &p, n);
+  if (rc) return rc;
+  h->d_scratch = p;
+  h->scratch_len = n;
+  return RTRG_OK;
+}
+
+int rtrg_extrap_P(rtrg_handle *h, int icosmo, const double *lnP3nk, double *P3np) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (!lnP3nk || !P3np) return fail(RTRG_EINVAL, "null argument");
+  const int nk = h->S.nk, np = h->S.np;
+  rc = hook_mask(h, icosmo);
+  if (rc) return rc;
+  double *yslot = h->S.ytmp + (size_t)icosmo * N_U * nk;
+  CU(cudaMemcpyAsync(yslot, lnP3nk, 3 * nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_extrap_only(h->tb, h->S, h->S.ytmp, (long long)N_U * nk, h->d_hookmask, h->stream), h->launches++;
+  CU(cudaMemcpyAsync(P3np, h->S.P3 + (size_t)icosmo * 3 * np, 3 * np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return RTRG_OK;
+}
+
+static int run_integrals_hook(rtrg_handle *h, int icosmo, const double *lnP3nk, bool want_raw) {
+  const int nk = h->S.nk;
+  int rc = hook_mask(h, icosmo);
+  if (rc) return rc;
+  if (want_raw && !h->d_raw) {
+    rc = dev_alloc(h->batch_allocs, &h->d_raw, (size_t)h->S.B * 190 * nk);
+    if (rc) return rc;
+  }
+  double *yslot = h->S.ytmp + (size_t)icosmo * N_U * nk;
+  CU(cudaMemcpyAsync(yslot, lnP3nk, 3 * nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)N_U * nk, h->S.src, want_raw ? h->d_raw : nullptr,
+                                  h->d_hookmask, h->cos[icosmo].c.sw_pr, 1, h->stream);
+  return RTRG_OK;
+}
+
+int rtrg_integrals_full(rtrg_handle *h, int icosmo, const double *lnP3nk, double *A64, double *R24, double *PTjm9,
+                        double *PMRn8) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (!lnP3nk) return fail(RTRG_EINVAL, "null argument");
+  const int nk = h->S.nk;
+  rc = run_integrals_hook(h, icosmo, lnP3nk, false);
+  if (rc) return rc;
+  std::vector<double> src((size_t)N_SRC * nk);
+  CU(cudaMemcpyAsync(src.data(), h->S.src + (size_t)icosmo * N_SRC * nk, src.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  if (A64) {  // 14 unique -> 64 slots with the symmetric copies (rt:147-157, 968-978)
+    static const int JU[14] = {8, 9, 10, 11, 12, 13, 14, 15, 56, 57, 59, 60, 61, 63};
+    static const int cp[10][2] = {{16, 8}, {18, 9}, {17, 10}, {19, 11}, {20, 12}, {22, 13}, {21, 14}, {23, 15}, {58, 57}, {62, 61}};
+    std::fill(A64, A64 + (size_t)64 * nk, 0.0);
+    for (int j = 0; j < 14; j++) std::copy(&src[(size_t)j * nk], &src[(size_t)(j + 1) * nk], A64 + (size_t)JU[j] * nk);
+    for (auto &q : cp) std::copy(A64 + (size_t)q[1] * nk, A64 + (size_t)(q[1] + 1) * nk, A64 + (size_t)q[0] * nk);
+  }
+  if (R24) std::copy(&src[(size_t)14 * nk], &src[(size_t)38 * nk], R24);
+  if (PTjm9) std::copy(&src[(size_t)38 * nk], &src[(size_t)47 * nk], PTjm9);
+  if (PMRn8) std::copy(&src[(size_t)47 * nk], &src[(size_t)55 * nk], PMRn8);
+  return RTRG_OK;
+}
+
+int rtrg_integrals_raw(rtrg_handle *h, int icosmo, const double *lnP3nk, double *J63, double *PZ63, double *Jn063,
+                       double *Jlo) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (!lnP3nk) return fail(RTRG_EINVAL, "null argument");
+  const int nk = h->S.nk;
+  rc = run_integrals_hook(h, icosmo, lnP3nk, true);
+  if (rc) return rc;
+  std::vector<double> raw((size_t)190 * nk);
+  CU(cudaMemcpyAsync(raw.data(), h->d_raw + (size_t)icosmo * 190 * nk, raw.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  if (J63) std::copy(&raw[0], &raw[(size_t)63 * nk], J63);
+  if (PZ63) std::copy(&raw[(size_t)63 * nk], &raw[(size_t)126 * nk], PZ63);
+  if (Jn063) std::copy(&raw[(size_t)126 * nk], &raw[(size_t)189 * nk], Jn063);
+  if (Jlo) *Jlo = raw[(size_t)189 * nk];
+  return RTRG_OK;
+}
+
+int rtrg_derivatives(rtrg_handle *h, int icosmo, double eta, const double *y, double *dy) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (!y || !dy) return fail(RTRG_EINVAL, "null argument");
+  const int nk = h->S.nk;
+  const size_t n = (size_t)N_U * nk;
+  rc = hook_mask(h, icosmo);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  double *yslot = h->S.ytmp + (size_t)icosmo * n;
+  CU(cudaMemcpyAsync(yslot, y, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->S.t + icosmo, &eta, sizeof(double), cudaMemcpyHostToDevice, st));
+  const Cosmo &c = h->cos[icosmo].c;
+  if (c.sw_nl && !c.sw_1l)
+    h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)n, h->S.src, nullptr, h->d_hookmask, c.sw_pr, 0, st);
+  launch_rhs(h->S, h->d_kgrid, h->S.ytmp, h->S.ynew, -1, h->d_hookmask, st), h->launches++;
+  CU(cudaMemcpyAsync(dy, h->S.ynew + (size_t)icosmo * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  return RTRG_OK;
+}
+
+int rtrg_D_dD(rtrg_handle *h, int icosmo, double z, const double *k, int n, double *D, double *dDda) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (n <= 0 || !k || !D || !dDda) return fail(RTRG_EINVAL, "bad argument");
+  rc = scratch(h, (size_t)3 * n);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  double *dk = h->d_scratch, *dD1 = dk + n, *dD2 = dk + 2 * n;
+  int zero = 0, err = 0;
+  CU(cudaMemcpyAsync(dk, k, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->d_err, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  launch_hook_DdD(h->S, icosmo, z, dk, n, dD1, dD2, h->d_err, st), h->launches++;
+  CU(cudaMemcpyAsync(D, dD1, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(dDda, dD2, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (err) return fail(RTRG_ERANGE, "D_dD: z=%g out of bounds (the reference aborts, hdr:646-649)", z);
+  return RTRG_OK;
+}
+
+int rtrg_Beta_P(rtrg_handle *h, int icosmo, double a, const double *k, int n, double *beta) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (n <= 0 || !k || !beta) return fail(RTRG_EINVAL, "bad argument");
+  rc = scratch(h, (size_t)2 * n);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  double *dk = h->d_scratch, *db = dk + n;
+  int zero = 0, err = 0;
+  CU(cudaMemcpyAsync(dk, k, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->d_err, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  launch_hook_beta(h->S, icosmo, a, dk, n, db, h->d_err, st), h->launches++;
+  CU(cudaMemcpyAsync(beta, db, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (err) return fail(RTRG_ERANGE, "Beta_P: a=%g > 1.001 (the reference aborts, hdr:528-531)", a);
+  return RTRG_OK;
+}
+
+int rtrg_Plin(rtrg_handle *h, int icosmo, int which, double z, const double *k, int n, double *P) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  if (n <= 0 || !k || !P || which < 0 || which > 2) return fail(RTRG_EINVAL, "bad argument");
+  rc = scratch(h, (size_t)2 * n);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  double *dk = h->d_scratch, *dp = dk + n;
+  CU(cudaMemcpyAsync(dk, k, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  launch_hook_plin(h->S, icosmo, which, z, dk, n, dp, st), h->launches++;
+  CU(cudaMemcpyAsync(P, dp, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  return RTRG_OK;
+}
+
+int rtrg_initial_state(rtrg_handle *h, int icosmo, double *y, double scal[2]) {
+  int rc = hook_check(h, icosmo);
+  if (rc) return rc;
+  const size_t n = (size_t)N_U * h->S.nk;
+  if (y) CU(cudaMemcpy(y, h->d_yinit + (size_t)icosmo * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (scal) {
+    scal[0] = h->cos[icosmo].c.Norm;
+    scal[1] = h->cos[icosmo].c.sigv2_0;
+  }
+  return RTRG_OK;
+}
+
+}  // extern "C"

@@ -35,7 +35,10 @@ double window_C(const GridSpec &g, int m);
 
 // The 14 bilinear kernels: 0..6 = J (alpha,-alpha,ell) (redTime.cc:731-732; n=1 regularised),
 //                          7..13 = Jn0 (redTime.cc:734-736)
+#ifndef RTRG_NKERN_DEFINED
+#define RTRG_NKERN_DEFINED
 enum { N_JKERN = 14, N_ZKERN = 7 };
+#endif
 struct KernSpec { int alpha, beta, ell; bool reg; };
 KernSpec kern_spec(int n);
 

@@ -1,0 +1,360 @@
+// Kernel family (1): the 1-loop mode-coupling integrals as dense quadratures over the
+// extrapolated log-k power spectrum (replaces redTime.cc:740-1282).
+//
+//   k_extrap    Pab extrapolation + window (rt:181-232, 772-778)            HBM/latency bound
+//   k_bilinear  J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]      FP64 FMA pipe bound
+//   k_jlo       J_0 at the low-k row nloMR (rt:1252,1267-1272)
+//   k_pz        P13-type log-convolutions PZ_n (rt:689-727)
+//   k_assemble  A_{acd,bef}, R^l_{abc}, P_T,jm, P_MR,n from the table of assembly_table.cc
+//
+// k_bilinear design (sm_100a): one CTA owns BIL_R = 8 consecutive output wavenumbers of one
+// kernel n of one cosmology.  Because T_n is circulant, rows i0..i0+7 read the same
+// (nsup+7)^2 window of T_n shifted along the diagonal, so each T element fetched from L2
+// feeds 8 rows x 3 spectra = 24 DFMAs.  The three spectra P q^2 (reversed and zero padded,
+// 8 KB) are staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); every
+// thread owns one alpha-side lag u, streams its T column with coalesced 8-byte loads that
+// are software-prefetched one 8-lag chunk ahead, and reads the beta-side window from
+// shared memory as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles.
+// Algorithmic work per (cosmology, n): 2*9*nk*nsup^2 FLOP; executed: 2*3*nk*(nsup+7)^2.
+#include <cstdint>
+
+#include "rtrg_device.h"
+
+namespace rtrg {
+
+// ---------------------------------------------------------------------------- helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// ---------------------------------------------------------------------------- k_extrap
+// y: state vectors [B][ystride]; only the three ln P components are read.
+__global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
+                         const double *__restrict__ y, long long ystride,
+                         double *__restrict__ P3, double *__restrict__ Prev,
+                         const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= tb.np) return;
+  const double *yb = y + (long long)b * ystride;
+  const int n0 = tb.ex_n0[ip];
+  const double w0 = tb.ex_w[4 * ip], w1 = tb.ex_w[4 * ip + 1], w2 = tb.ex_w[4 * ip + 2],
+               w3 = tb.ex_w[4 * ip + 3];
+  const double tail = (cosmo[b].ns - 3.0) * tb.ex_dx[ip];
+  const double win = tb.WP[ip], kk = tb.kpad[ip], k2 = kk * kk;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const double *f = yb + c * tb.nk + n0;
+    double lnP = tail;
+    if (w0 != 0.0) lnP += w0 * f[0];
+    if (w1 != 0.0) lnP += w1 * f[1];
+    if (w2 != 0.0) lnP += w2 * f[2];
+    if (w3 != 0.0) lnP += w3 * f[3];
+    const double P = (win > 0.0) ? exp(lnP) * win : 0.0;
+    P3[((long long)b * 3 + c) * tb.np + ip] = P;
+    if (ip >= tb.jlo)
+      Prev[((long long)b * 3 + c) * tb.LP + (BIL_R - 1) + (tb.np - 1 - ip)] = P * k2;
+  }
+}
+
+// ---------------------------------------------------------------------------- k_bilinear
+template <int R, int TPB>
+__global__ void __launch_bounds__(TPB)
+    k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+               double *__restrict__ Jpart, int n_first, int row0, const int *__restrict__ mask) {
+  const int e = blockIdx.z;
+  if (mask && !mask[e]) return;
+  const int n = n_first + blockIdx.y;
+  if (n >= 7 && !cosmo[e].sw_pr) return;  // Jn0 only feeds the RSD terms (rt:804)
+  const int rb = blockIdx.x / tb.nchunk, chunk = blockIdx.x - rb * tb.nchunk;
+  extern __shared__ __align__(128) double sm[];
+  double *s_a = sm;                // [3][LP]
+  double *s_red = sm + 3 * tb.LP;  // [TPB/32][9R]
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int LP = tb.LP, ldT = tb.ldT;
+  const uint32_t bytes = 3u * (uint32_t)LP * 8u;
+
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&mbar, bytes);
+    tma_bulk_g2s(s_a, Prev + (long long)e * 3 * LP, bytes, &mbar);
+  }
+
+  const int i0 = row0 + rb * R;
+  const int tu = chunk * TPB + tid;
+  const bool active = tu < tb.NV;
+  const int tuc = active ? tu : tb.NV - 1;
+  const double *Tp = tb.Tc + ((size_t)n * tb.NUp + i0) * ldT + i0 + tuc;
+
+  double acc[R][3];
+#pragma unroll
+  for (int r = 0; r < R; r++) acc[r][0] = acc[r][1] = acc[r][2] = 0.0;
+  double tcur[R], tnxt[R];
+#pragma unroll
+  for (int s = 0; s < R; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
+
+  mbar_wait(&mbar, 0);
+
+  const int NVp = tb.NVp;
+  for (int tv0 = 0; tv0 < NVp; tv0 += R) {
+    if (tv0 + R < NVp) {
+      const double *Tn = Tp + (size_t)(tv0 + R) * ldT;
+#pragma unroll
+      for (int s = 0; s < R; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      // window w[q] = arev_c[tv0 + q - (R-1)], q in [0, 2R-1): 16-byte broadcast loads
+      double w[2 * R];
+      const double2 *wp = reinterpret_cast<const double2 *>(s_a + c * LP + tv0);
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const double2 v = wp[q];
+        w[2 * q] = v.x;
+        w[2 * q + 1] = v.y;
+      }
+#pragma unroll
+      for (int s = 0; s < R; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r][c] = fma(tcur[s], w[s - r + R - 1], acc[r][c]);
+    }
+#pragma unroll
+    for (int s = 0; s < R; s++) tcur[s] = tnxt[s];
+  }
+
+  // alpha side: out[r][ab][cd] = sum_u arev_ab[u - r] * S_u[r][cd]
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+#pragma unroll
+    for (int ab = 0; ab < 3; ab++) {
+      const double m = active ? s_a[ab * LP + (R - 1) + tu - r] : 0.0;
+#pragma unroll
+      for (int cd = 0; cd < 3; cd++) {
+        const double x = warp_sum(m * acc[r][cd]);
+        if (lane == 0) s_red[warp * (9 * R) + (ab * 3 + cd) * R + r] = x;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 9 * R) {
+    double s = 0.0;
+#pragma unroll 1
+    for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
+    const int pair = tid / R, r = tid - pair * R;
+    Jpart[((((long long)e * N_JKERN + n) * tb.nchunk + chunk) * 9 + pair) * tb.nk + i0 + r] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------- k_jlo
+// J_{000}(P00,P00) at the padded row nloMR, needed by P_MR,4..6 (rt:1252,1267-1272)
+__global__ void __launch_bounds__(256)
+    k_jlo(IntegralTabs tb, double kfac_lo, const double *__restrict__ Prev,
+          double *__restrict__ Jlo, const int *__restrict__ mask) {
+  const int e = blockIdx.x;
+  if (mask && !mask[e]) return;
+  extern __shared__ double s_p[];  // [nsup]
+  __shared__ double s_w[8];
+  const double *a = Prev + (long long)e * 3 * tb.LP + (BIL_R - 1);
+  for (int j = threadIdx.x; j < tb.nsup; j += blockDim.x) s_p[j] = a[j];
+  __syncthreads();
+  double tot = 0.0;
+  for (int jj = threadIdx.x; jj < tb.nsup; jj += blockDim.x) {
+    double acc = 0.0;
+    const double *Tc = tb.Tlo + jj;
+    for (int ll = 0; ll < tb.nsup; ll++) acc = fma(__ldg(Tc + (size_t)ll * tb.nsup), s_p[ll], acc);
+    tot += acc * s_p[jj];
+  }
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) s += s_w[wv];
+    Jlo[e] = kfac_lo * s;
+  }
+}
+
+// ---------------------------------------------------------------------------- k_pz
+// PZb[e][n][ab][i] = dlnk/(2 pi^2) k_i^3 P00(k_i) sum_m P_ab(q_m) G_n[i_pad - m]
+__global__ void __launch_bounds__(128)
+    k_pz(IntegralTabs tb, double pre, const double *__restrict__ P3, double *__restrict__ PZb,
+         int row0, int nrows, const int *__restrict__ mask) {
+  const int e = blockIdx.y;
+  if (mask && !mask[e]) return;
+  const int n = blockIdx.x / 3, ab = blockIdx.x - 3 * n;
+  extern __shared__ double s_p[];  // [np]
+  const double *Pab = P3 + ((long long)e * 3 + ab) * tb.np;
+  for (int m = threadIdx.x; m < tb.np; m += blockDim.x) s_p[m] = Pab[m];
+  __syncthreads();
+  const double *G = tb.G + (long long)n * (2 * tb.np - 1) + (tb.np - 1);
+  for (int ii = threadIdx.x; ii < nrows; ii += blockDim.x) {
+    const int i = row0 + ii, ipad = tb.nshift + i;
+    double acc = 0.0;
+    for (int m = tb.jlo; m < tb.np; m++) acc = fma(s_p[m], __ldg(G + ipad - m), acc);
+    const double k = tb.kpad[ipad];
+    PZb[(((long long)e * N_ZKERN + n) * 3 + ab) * tb.nk + i] =
+        pre * (k * k * k) * P3[(long long)e * 3 * tb.np + ipad] * acc;
+  }
+}
+
+// ---------------------------------------------------------------------------- k_assemble
+__device__ __forceinline__ double kpow_i(double k, double kinv, int p) {
+  double r = 1.0;
+  if (p > 0)
+    for (int i = 0; i < p; i++) r *= k;
+  else
+    for (int i = 0; i < -p; i++) r *= kinv;
+  return r;
+}
+enum { ASM_ROWS = 16, ASM_NV = 190 };
+__global__ void __launch_bounds__(256)
+    k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
+               const double *__restrict__ PZb, const double *__restrict__ P3,
+               const double *__restrict__ Jlo, double *__restrict__ src, double *__restrict__ raw,
+               int row0, int nrows, const int *__restrict__ mask) {
+  const int e = blockIdx.y;
+  if (mask && !mask[e]) return;
+  __shared__ double vals[ASM_NV][ASM_ROWS + 1];
+  const int r0 = row0 + blockIdx.x * ASM_ROWS;
+  const int rows = min(ASM_ROWS, row0 + nrows - r0);
+  const int has_jn0 = cosmo[e].sw_pr;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < ASM_NV * ASM_ROWS; idx += blockDim.x) {
+    const int v = idx / ASM_ROWS, rr = idx - v * ASM_ROWS;
+    if (rr >= rows) continue;
+    const int i = r0 + rr, ipad = tb.nshift + i;
+    double x = 0.0;
+    if (v < 63 || (v >= 126 && v < 189)) {
+      const int iJ = (v < 63) ? v : v - 126;
+      const int n = iJ / 9 + ((v < 63) ? 0 : 7), pair = iJ % 9;
+      if (v < 63 || has_jn0) {
+        for (int ch = 0; ch < tb.nchunk; ch++)
+          x += Jpart[((((long long)e * N_JKERN + n) * tb.nchunk + ch) * 9 + pair) * tb.nk + i];
+        x *= tb.kfac[n * tb.nk + i];
+      }
+    } else if (v < 126) {
+      const int iJ = v - 63, n = iJ / 9, ab = (iJ % 9) / 3, cd = iJ % 3;
+      x = PZb[(((long long)e * N_ZKERN + n) * 3 + ab) * tb.nk + i];
+      if (cd) {  // rt:797-800
+        const double *P = P3 + (long long)e * 3 * tb.np;
+        x = x * P[cd * tb.np + ipad] / (P[ipad] + 1e-100);
+      }
+    } else {
+      x = Jlo[e];
+    }
+    vals[v][rr] = x;
+    if (raw) raw[((long long)e * ASM_NV + v) * tb.nk + i] = x;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N_SRC * ASM_ROWS; idx += blockDim.x) {
+    const int o = idx / ASM_ROWS, rr = idx - o * ASM_ROWS;
+    if (rr >= rows) continue;
+    const int i = r0 + rr;
+    const double k = tb.kgrid[i], kinv = 1.0 / k;
+    double acc = 0.0;
+    const int t1 = tb.t_start[o + 1];
+    for (int t = tb.t_start[o]; t < t1; t++) {
+      const int s = tb.t_src[t];
+      const int v = (s == 3) ? 189 : s * 63 + tb.t_index[t];
+      acc += tb.t_coef[t] * kpow_i(k, kinv, tb.t_kpow[t]) * vals[v][rr];
+    }
+    src[((long long)e * N_SRC + o) * tb.nk + i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------- launchers
+enum { BIL_TPB = 352 };
+
+size_t bilinear_smem_bytes(const IntegralTabs &tb) {
+  return (size_t)(3 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
+}
+
+// Full evaluation for every (unmasked) cosmology: y -> src (and optionally raw J/PZ/Jn0).
+// Returns the number of kernel launches.
+int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
+                     double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
+                     cudaStream_t st) {
+  const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
+  int launches = 0;
+  {
+    dim3 g((tb.np + 127) / 128, B);
+    k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask);
+    launches++;
+  }
+  {
+    const int nkern = with_jn0 ? N_JKERN : 7;
+    dim3 g((nrows / BIL_R) * tb.nchunk, nkern, B);
+    k_bilinear<BIL_R, BIL_TPB>
+        <<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+    launches++;
+  }
+  if (with_jlo) {
+    k_jlo<<<B, 256, tb.nsup * sizeof(double), st>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
+    launches++;
+  }
+  {
+    dim3 g(N_ZKERN * 3, B);
+    const double pre = tb.dlnk / (2.0 * M_PI * M_PI);  // rt:719
+    k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask);
+    launches++;
+  }
+  {
+    dim3 g((nrows + ASM_ROWS - 1) / ASM_ROWS, B);
+    k_assemble<<<g, 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
+                                  nrows, mask);
+    launches++;
+  }
+  return launches;
+}
+
+void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
+                        const int *mask, cudaStream_t st) {
+  dim3 g((tb.np + 127) / 128, S.B);
+  k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask);
+}
+
+int integrals_configure() {
+  // opt in to the dynamic shared memory the bilinear kernel may need for large grids
+  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+}  // namespace rtrg

@@ -1,0 +1,291 @@
+// Kernel family (4): linear-theory tables and look-ups, all on the device.
+//
+//   k_beta_reduce   Beta_P(a,k) table pre-reduced in k   (hdr:513-637, tab:262-328)
+//   k_growth_ode    scale-dependent growth tables: one thread integrates one wavenumber
+//                   through n_lna+1 legs with RK8PD + GSL step control (hdr:133-190,690-710)
+//   k_growth_norm / k_growth_rows   Dnorm and per-grid-k rows (hdr:712-729)
+//   k_tgrid         CAMB transfer function at the grid wavenumbers (hdr:790-832)
+//   k_qag           sigma_8 normalisation and sigma_v^2 by QAG-61: one warp per cosmology,
+//                   lanes evaluate the 61 (122) abscissae, lane 0 runs QUADPACK's bisection
+//                   bookkeeping in shared memory (hdr:846-879, 932-963)
+//   k_init_state    initial conditions and the z1l linear spectrum (rt:1570-1586, 1299-1306)
+//   k_hook_*        stage-level parity hooks (D_dD, Beta_P, Plin*)
+#include "gk61_table.h"
+#include "rtrg_device.h"
+
+namespace rtrg {
+
+__constant__ PDTableau c_pd;
+__constant__ double c_xgk[31], c_wgk[31], c_wg[15];
+
+int linear_upload_constants() {
+  const PDTableau pd = make_pd_tableau();
+  cudaError_t e = cudaMemcpyToSymbol(c_pd, &pd, sizeof(pd));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyToSymbol(c_xgk, gk61_xgk, sizeof(gk61_xgk));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyToSymbol(c_wgk, gk61_wgk, sizeof(gk61_wgk));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyToSymbol(c_wg, gk61_wg, sizeof(gk61_wg));
+  return (int)e;
+}
+
+// wavenumber of slot kk of the reduced beta table: nk grid values, then the growth-table ones
+__device__ __forceinline__ double slot_k(const Batch &S, const double *kgrid, int kk) {
+  return kk < S.nk ? kgrid[kk] : exp(S.lnkg[kk - S.nk]);
+}
+
+__global__ void k_beta_reduce(Batch S, const double *__restrict__ kgrid) {
+  const int b = blockIdx.y, kk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= S.nkk) return;
+  const Cosmo &c = S.cosmo[b];
+  double *out = S.bred + (long long)b * S.n_zmax * S.nkk + kk;
+  if (c.n_z == 0 || c.On / c.Om < 1e-10) {
+    for (int j = 0; j < S.n_zmax; j++) out[(long long)j * S.nkk] = 0.0;
+    return;
+  }
+  double k = slot_k(S, kgrid, kk);
+  if (k < S.beta_kmin) k = S.beta_kmin;  // hdr:538-545
+  if (k > S.beta_kmax) k = S.beta_kmax;
+  const BetaTab t = beta_tab(S, c);
+  const Stencil st = tab_stencil_y(t.k, t.n_kb, k);
+  for (int j = 0; j < c.n_z; j++)
+    out[(long long)j * S.nkk] = stencil_apply(st, t.beta + (long long)j * t.n_kb);
+  for (int j = c.n_z; j < S.n_zmax; j++) out[(long long)j * S.nkk] = 0.0;
+}
+
+__global__ void __launch_bounds__(64) k_growth_ode(Batch S) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > S.n_lnk) return;
+  const Cosmo &c = S.cosmo[b];
+  GrowthCtx g;
+  g.bg = bg_static(c);
+  g.bt = beta_tab(S, c);
+  g.brow = S.bred + (long long)b * S.n_zmax * S.nkk + (S.nk + j);
+  g.bstride = S.nkk;
+  const int nj = S.n_lnk + 1;
+  double *G = S.G + (long long)b * (S.n_lna + 1) * nj, *dD = S.dD + (long long)b * (S.n_lna + 1) * nj;
+  double y[2] = {1.0, 1.0 / S.a_early};  // hdr:697-698
+  growth_integrate(c_pd, g, S.a_early, GROWTH_A_MIN, y);
+  G[j] = y[0] / GROWTH_A_MIN;
+  dD[j] = y[1];
+  for (int i = 1; i <= S.n_lna; i++) {
+    const double a1 = exp(S.lna[i]);
+    growth_integrate(c_pd, g, exp(S.lna[i - 1]), a1, y);
+    G[(long long)i * nj + j] = y[0] / a1;
+    dD[(long long)i * nj + j] = y[1];
+  }
+}
+
+__global__ void k_growth_norm(Batch S) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > S.n_lnk) return;
+  const GrowthTab t = growth_tab(S, b);
+  // DnormTab[j] = G_lna_lnk(0, lnkTab[j])  (hdr:716-717)
+  S.Dnorm[(long long)b * (S.n_lnk + 1) + j] =
+      tab2d(t.lna, t.n_lna + 1, t.lnk, t.n_lnk + 1, t.G, 0.0, t.lnk[j]);
+}
+
+__global__ void k_growth_rows(Batch S, const double *__restrict__ kgrid) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.nk) return;
+  const GrowthTab t = growth_tab(S, b);
+  double k = kgrid[i];
+  if (k > GROWTH_K_MAX) k = GROWTH_K_MAX;
+  if (k < GROWTH_K_MIN) k = GROWTH_K_MIN;
+  const double lnk0 = log(k);
+  S.D0row[(long long)b * S.nk + i] = tab1d(t.lnk, t.Dnorm, t.n_lnk + 1, lnk0);
+  const Stencil st = tab_stencil_y(t.lnk, t.n_lnk + 1, lnk0);
+  const int nj = S.n_lnk + 1;
+  for (int ia = 0; ia <= S.n_lna; ia++) {
+    const long long o = ((long long)b * (S.n_lna + 1) + ia) * S.nk + i;
+    S.Grow[o] = stencil_apply(st, t.G + (long long)ia * nj);
+    S.dDrow[o] = stencil_apply(st, t.dD + (long long)ia * nj);
+  }
+}
+
+__global__ void k_tgrid(Batch S, const double *__restrict__ kgrid) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.nk) return;
+  const LinCtx L = lin_ctx(S, b);
+  S.Tgrid[(long long)b * S.nk + i] = transfer_cb(L, kgrid[i]);
+}
+
+// ---- QAG-61, one warp per cosmology ---------------------------------------------------
+template <int WHICH>
+__device__ __forceinline__ double qag_integrand(const LinCtx &L, double x) {
+  return WHICH == 0 ? sigma8_integrand(L, x) : sigmav_integrand(L, x);
+}
+template <int WHICH>
+__device__ double qag_warp(const LinCtx &L, QagState &w, double *fv, double *iv, int *status) {
+  const int lane = threadIdx.x & 31;
+  const double x0 = -15, x1 = 15, epsabs = 0, epsrel = 1e-4;  // hdr:853-854, 942-943
+  const int limit = 1000;
+  for (int s = lane; s < 61; s += 32) fv[s] = qag_integrand<WHICH>(L, qk61_abscissa(c_xgk, x0, x1, s));
+  __syncwarp();
+  int done = 0;
+  if (lane == 0) {
+    const Qk61Out q0 = qk61_combine(c_xgk, c_wgk, c_wg, x0, x1, fv);
+    done = qag_begin(w, x0, x1, epsabs, epsrel, q0) ? 1 : 0;
+    if (!done) qag_next(w, &iv[0], &iv[1], &iv[2], &iv[3]);
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  while (!done) {
+    __syncwarp();
+    for (int s = lane; s < 122; s += 32) {
+      const int half = s >= 61;
+      fv[s] = qag_integrand<WHICH>(L, qk61_abscissa(c_xgk, iv[2 * half], iv[2 * half + 1], s - 61 * half));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const Qk61Out q1 = qk61_combine(c_xgk, c_wgk, c_wg, iv[0], iv[1], fv);
+      const Qk61Out q2 = qk61_combine(c_xgk, c_wgk, c_wg, iv[2], iv[3], fv + 61);
+      done = qag_update(w, q1, q2, limit) ? 1 : 0;
+      if (!done) qag_next(w, &iv[0], &iv[1], &iv[2], &iv[3]);
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+  }
+  double r = 0;
+  if (lane == 0) {
+    r = qag_result(w);
+    if (w.done == 3 || w.error_type) *status = RTRG_QAG_FAIL;
+  }
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+
+__global__ void __launch_bounds__(32) k_qag(Batch S) {
+  const int b = blockIdx.x;
+  __shared__ QagState w;
+  __shared__ double fv[122];
+  __shared__ double iv[4];
+  __shared__ int st;
+  if (threadIdx.x == 0) st = 0;
+  __syncwarp();
+  Cosmo &c = S.cosmo[b];
+  const LinCtx L = lin_ctx(S, b);
+  const double r8 = qag_warp<0>(L, w, fv, iv, &st);
+  if (threadIdx.x == 0) c.Norm = c.s8 * c.s8 / r8;  // hdr:874
+  __threadfence_block();
+  __syncwarp();
+  const double rv = qag_warp<1>(L, w, fv, iv, &st);
+  if (threadIdx.x == 0) {
+    c.sigv2_0 = rv / (6.0 * M_PI * M_PI);  // hdr:961
+    if (st) c.status = st;
+  }
+}
+
+// ---- per grid-wavenumber linear quantities through the pre-reduced rows ----------------
+struct RowLin {
+  double D, dD, beta;
+  bool ok;
+};
+__device__ __forceinline__ double row_beta(const Batch &S, int b, int i, double a) {
+  const Cosmo &c = S.cosmo[b];
+  const BetaTab t = beta_tab(S, c);
+  return beta_row(t, S.bred + (long long)b * S.n_zmax * S.nkk + i, a, S.nkk);
+}
+__device__ __forceinline__ bool row_D_dD(const Batch &S, int b, int i, double z, double *D, double *dD) {
+  const long long o = (long long)b * (S.n_lna + 1) * S.nk + i;
+  return growth_D_dD_row(S.lna, S.n_lna, S.Grow + o, S.dDrow + o, S.nk, S.D0row[(long long)b * S.nk + i], z,
+                         D, dD);
+}
+// Plin / Plin_cb / Plin_nu at a grid wavenumber (hdr:881-930)
+__device__ __forceinline__ double row_plin(const Batch &S, int b, int i, double k, double z, int which,
+                                           double *D_out, double *dD_out) {
+  const Cosmo &c = S.cosmo[b];
+  const double a = 1.0 / (1.0 + z), fn = c.On / c.Om, fc = 1.0 - fn;
+  const double T = S.Tgrid[(long long)b * S.nk + i];
+  const double B = row_beta(S, b, i, a);
+  const double F = 1.0 - fn + B;
+  double D = NAN, dD = NAN;
+  row_D_dD(S, b, i, z, &D, &dD);
+  if (D_out) *D_out = D;
+  if (dD_out) *dD_out = dD;
+  const double P = c.Norm * pow(k, c.ns) * T * T * F * F * D * D;
+  if (which == 0) return P;
+  if (which == 1) {
+    if (fn <= 1e-10) return P;
+    const double Rr = 1.0 / (fc + B);
+    return P * Rr * Rr;
+  }
+  if (fn <= 1e-10) return 0.0;
+  const double Rr = B / fn / (fc + B);
+  return P * Rr * Rr;
+}
+
+__global__ void k_init_state(Batch S, const double *__restrict__ kgrid) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.nk) return;
+  const Cosmo &c = S.cosmo[b];
+  const int nk = S.nk;
+  const double k = kgrid[i];
+  double D = 0, dD = 0;
+  const double Pin = row_plin(S, b, i, k, c.z_in, 1, &D, &dD);
+  const double f_in = c.a_in * dD / D;  // rt:1576
+  double *y = S.y + (long long)b * N_U * nk;
+  y[i] = log(Pin);
+  y[nk + i] = log(Pin * f_in);
+  y[2 * nk + i] = log(Pin * f_in * f_in);
+  for (int j = N_UP; j < N_U; j++) y[j * nk + i] = 0.0;
+  // linear spectrum at z1l for the 1-loop cache (rt:1299-1306)
+  double Dz = 0;
+  const double Pz = row_plin(S, b, i, k, S.z1l, 1, &Dz, nullptr);
+  S.D_z1l[(long long)b * nk + i] = Dz;
+  const double l = log(Pz);
+  double *yz = S.y_z1l + (long long)b * 3 * nk;
+  yz[i] = l;
+  yz[nk + i] = l;
+  yz[2 * nk + i] = l;
+}
+
+// ---- hooks -------------------------------------------------------------------------------
+__global__ void k_hook_DdD(Batch S, int b, double z, const double *k, int n, double *D, double *dD,
+                           int *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GrowthTab t = growth_tab(S, b);
+  if (!growth_D_dD(t, z, k[i], &D[i], &dD[i])) *err = 1;
+}
+__global__ void k_hook_beta(Batch S, int b, double a, const double *k, int n, double *beta, int *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const BetaTab t = beta_tab(S, S.cosmo[b]);
+  const double v = beta_P(t, a, k[i]);
+  beta[i] = v;
+  if (v != v) *err = 1;
+}
+__global__ void k_hook_plin(Batch S, int b, int which, double z, const double *k, int n, double *P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const LinCtx L = lin_ctx(S, b);
+  P[i] = which == 0 ? plin(L, z, k[i]) : which == 1 ? plin_cb(L, z, k[i]) : plin_nu(L, z, k[i]);
+}
+
+// ---- launch sequence of the device-side initialisation ----------------------------------
+int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st) {
+  int n = 0;
+  const int B = S.B;
+  k_beta_reduce<<<dim3((S.nkk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;
+  k_growth_norm<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;
+  k_growth_rows<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  k_tgrid<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  k_qag<<<B, 32, 0, st>>>(S), n++;
+  k_init_state<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  return n;
+}
+
+void launch_hook_DdD(const Batch &S, int b, double z, const double *k, int n, double *D, double *dD,
+                     int *err, cudaStream_t st) {
+  k_hook_DdD<<<(n + 127) / 128, 128, 0, st>>>(S, b, z, k, n, D, dD, err);
+}
+void launch_hook_beta(const Batch &S, int b, double a, const double *k, int n, double *beta, int *err,
+                      cudaStream_t st) {
+  k_hook_beta<<<(n + 127) / 128, 128, 0, st>>>(S, b, a, k, n, beta, err);
+}
+void launch_hook_plin(const Batch &S, int b, int which, double z, const double *k, int n, double *P,
+                      cudaStream_t st) {
+  k_hook_plin<<<(n + 127) / 128, 128, 0, st>>>(S, b, which, z, k, n, P);
+}
+
+}  // namespace rtrg

@@ -1,0 +1,371 @@
+// Kernel families (2) and (3): the Time-RG right-hand side and the batched, device-resident
+// adaptive RKF45 stepper (replaces redTime.cc:1383-1547 and the gsl_odeiv driver loop of
+// redTime.cc:1588-1632), plus the output assembly (redTime.cc:1634-1742).
+//
+// One integrator per cosmology.  All cosmologies advance in lock step over *attempt
+// index*: every round each unfinished cosmology either attempts one RKF45 step with its
+// own step size, or emits one output table.  The per-cosmology accept / reject / clip
+// decisions follow gsl_odeiv_evolve_apply + std_control_hadjust exactly;
+// they are taken on the device by k_ctrl_begin / k_ctrl_end, so no host round trip is
+// needed inside a step.  State vectors stay in HBM in the reference's component-major
+// layout; the error norm is a max over all 41 nk components (order independent).
+//
+//   k_rhs        dy = f(eta, y)                     HBM bound: 960 nk bytes per evaluation
+//   k_combine    ytmp = y + h sum_j a_sj k_j
+//   k_final      5th-order solution, error estimate, rmax = max |yerr|/(eps_rel |y| + eps_abs)
+//   k_accept     y <- ynew for accepted cosmologies
+//   k_output     one nk x ncols table
+#include "rtrg_device.h"
+
+namespace rtrg {
+
+// linear quantities at grid wavenumber i through the pre-reduced rows (see kernels_linear.cu)
+__device__ __forceinline__ double ode_row_beta(const Batch &S, int b, int i, double a) {
+  const BetaTab t = beta_tab(S, S.cosmo[b]);
+  return beta_row(t, S.bred + (long long)b * S.n_zmax * S.nkk + i, a, S.nkk);
+}
+__device__ __forceinline__ bool ode_row_D_dD(const Batch &S, int b, int i, double z, double *D,
+                                             double *dD) {
+  const long long o = (long long)b * (S.n_lna + 1) * S.nk + i;
+  return growth_D_dD_row(S.lna, S.n_lna, S.Grow + o, S.dDrow + o, S.nk,
+                         S.D0row[(long long)b * S.nk + i], z, D, dD);
+}
+
+// ---------------------------------------------------------------------------- k_rhs
+// stage < 0: eta = t[b]; otherwise eta = t[b] + c_stage * h_try[b].
+__global__ void __launch_bounds__(128)
+    k_rhs(Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv,
+          double *__restrict__ dyv, int stage, const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.k_hi) return;
+  const Cosmo &c = S.cosmo[b];
+  const int nk = S.nk;
+  const double eta = (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b];
+  const double A = c.a_in * exp(eta);  // rt:1430
+  const double k = kgrid[i];
+
+  double y[N_U], dy[N_U];
+  const double *yb = yv + (long long)b * N_U * nk + i;
+#pragma unroll
+  for (int j = 0; j < N_U; j++) y[j] = yb[(long long)j * nk];
+
+  double Om10, Om11;
+  trg_omega(c, A, ode_row_beta(S, b, i, A), &Om10, &Om11);
+
+  double A14[N_UI], R24[N_UQ];
+  const int evolve_Q = (S.print_Q || c.sw_pr);
+  if (c.sw_nl) {
+    if (c.sw_1l) {
+      // rescale the z1l cache (rt:1316-1337)
+      const double z = exp(-eta) * (1.0 + c.z_in) - 1;
+      double D = 0, dD = 0;
+      ode_row_D_dD(S, b, i, z, &D, &dD);
+      const double fz = dD / (D * (1.0 + z));
+      const double rD = D / S.D_z1l[(long long)b * nk + i];
+      const double pre = (rD * rD) * (rD * rD) * exp(-4.0 * eta);
+      const double *s1 = S.src_z1l + (long long)b * N_SRC * nk + i;
+      double fp[5];
+      fp[0] = 1.0;
+#pragma unroll
+      for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
+#pragma unroll
+      for (int j = 0; j < N_UI; j++) A14[j] = pre * fp[a14_fpow(j)] * s1[(long long)j * nk];
+#pragma unroll
+      for (int j = 0; j < N_UQ; j++)
+        R24[j] = evolve_Q ? pre * fp[r24_fpow(j)] * s1[(long long)(N_UI + j) * nk] : 0.0;
+    } else {
+      const double *s1 = S.src + (long long)b * N_SRC * nk + i;
+#pragma unroll
+      for (int j = 0; j < N_UI; j++) A14[j] = s1[(long long)j * nk];
+#pragma unroll
+      for (int j = 0; j < N_UQ; j++) R24[j] = evolve_Q ? s1[(long long)(N_UI + j) * nk] : 0.0;
+    }
+  }
+  trg_rhs_row(eta, k, Om10, Om11, c.sw_nl, evolve_Q, y, A14, R24, dy);
+  double *db = dyv + (long long)b * N_U * nk + i;
+#pragma unroll
+  for (int j = 0; j < N_U; j++) db[(long long)j * nk] = dy[j];
+}
+
+// ---------------------------------------------------------------------------- k_combine
+__global__ void k_combine(Batch S, int stage, const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const long long n = (long long)N_U * S.nk;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const long long o = (long long)b * n + idx, ks = (long long)S.B * n;
+  double acc = 0.0;
+  for (int j = 0; j < stage; j++) {
+    const double a = RKF45::a(stage, j);
+    if (a != 0.0) acc += a * S.kst[j * ks + o];
+  }
+  S.ytmp[o] = S.y[o] + S.h_try[b] * acc;
+}
+
+// ---------------------------------------------------------------------------- k_final
+__global__ void __launch_bounds__(256) k_final(Batch S, const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const long long n = (long long)N_U * S.nk;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0;
+  if (idx < n) {
+    const long long o = (long long)b * n + idx, ks = (long long)S.B * n;
+    const double h = S.h_try[b];
+    double acc = 0.0, err = 0.0;
+#pragma unroll
+    for (int j = 0; j < RK_STAGES; j++) {
+      const double kj = S.kst[j * ks + o];
+      if (RKF45::b(j) != 0.0) acc += RKF45::b(j) * kj;
+      if (RKF45::e(j) != 0.0) err += RKF45::e(j) * kj;
+    }
+    const double yn = S.y[o] + h * acc, ye = h * err;
+    S.ynew[o] = yn;
+    S.yerr[o] = ye;
+    // only rows owned by this rank contribute (k-sharding); all rows otherwise
+    const int i = (int)(idx % S.nk);
+    if (i >= S.k_lo && i < S.k_hi) {
+      const double D0 = S.eps_rel * fabs(yn) + S.eps_abs;
+      r = fabs(ye) / fabs(D0);
+      if (!(r == r)) r = 0.0;  // GSL_MAX_DBL ignores NaN
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  __shared__ double s_r[8];
+  if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, s_r[w]);
+    atomicMax(&S.rmax_bits[b], (unsigned long long)__double_as_longlong(r));
+  }
+}
+
+// ---------------------------------------------------------------------------- control
+// has_full: some cosmology runs the full Time-RG (integrals inside the RHS).
+__global__ void k_ctrl_begin(Batch S) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  S.flag_out[b] = S.flag_step[b] = S.flag_acc[b] = 0;
+  S.m_full_step[b] = S.m_full_acc[b] = S.m_out_int[b] = 0;
+  if (S.done[b]) return;
+  const Cosmo &c = S.cosmo[b];
+  const double target = S.etaout[(long long)b * MAX_OUT + S.i_out[b]];
+  const double t = S.t[b], h = S.h[b];
+  if ((target - t) * h > 0) {  // rt:1614
+    double h0 = h;
+    const double dt = target - t;
+    int fin = 0;
+    if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) {
+      h0 = dt;
+      fin = 1;
+    }
+    S.h_try[b] = h0;
+    S.final_step[b] = fin;
+    S.flag_step[b] = 1;
+    S.m_full_step[b] = (c.sw_nl && !c.sw_1l);
+    S.rmax_bits[b] = (unsigned long long)__double_as_longlong(DBL_MIN);
+  } else {
+    S.flag_out[b] = 1;
+    S.m_out_int[b] = (c.sw_nl && c.sw_1l);  // rt:1646
+  }
+}
+
+__global__ void k_ctrl_end(Batch S, int max_attempts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  if (S.done[b]) return;
+  Cosmo &c = S.cosmo[b];
+  long long *cnt = S.counters + 4LL * b;
+  if (S.flag_out[b]) {
+    S.i_out[b]++;
+    if (S.i_out[b] >= c.n_out) {
+      S.done[b] = 1;
+      atomicSub(S.n_active, 1);
+    }
+    return;
+  }
+  if (!S.flag_step[b]) return;
+  const double rmax = __longlong_as_double((long long)S.rmax_bits[b]);
+  const double target = S.etaout[(long long)b * MAX_OUT + S.i_out[b]];
+  const double h_old = S.h_try[b];
+  const double t_new = S.final_step[b] ? target : S.t[b] + h_old;
+  cnt[0]++;
+  cnt[2] += 5;
+  double h0 = h_old;
+  const int adj = gsl_hadjust(rmax, 5, &h0);
+  if (adj == -1) {
+    const double t_next = t_new + h0;
+    if (fabs(h0) < fabs(h_old) && t_next != t_new) {
+      S.h[b] = h0;  // rejected: retry from the same (t, y) with the smaller step
+      cnt[1]++;
+      if (cnt[0] >= max_attempts) {
+        c.status = RTRG_ODE_FAIL;
+        S.done[b] = 1;
+        atomicSub(S.n_active, 1);
+      }
+      return;
+    }
+    h0 = h_old;
+  }
+  S.t[b] = t_new;
+  S.h[b] = h0;
+  S.flag_acc[b] = 1;
+  S.m_full_acc[b] = (c.sw_nl && !c.sw_1l);
+  cnt[2] += 1;
+  if (cnt[0] >= max_attempts) {
+    c.status = RTRG_ODE_FAIL;
+    S.done[b] = 1;
+    atomicSub(S.n_active, 1);
+  }
+}
+
+__global__ void k_accept(Batch S) {
+  const int b = blockIdx.y;
+  if (!S.flag_acc[b]) return;
+  const long long n = (long long)N_U * S.nk;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  S.y[(long long)b * n + idx] = S.ynew[(long long)b * n + idx];
+}
+
+// ---------------------------------------------------------------------------- k_output
+// columns of one row as in rt:1670-1737
+__global__ void __launch_bounds__(128) k_output(Batch S, const double *__restrict__ kgrid) {
+  const int b = blockIdx.y;
+  if (!S.flag_out[b]) return;
+  const Cosmo &c = S.cosmo[b];
+  const int nk = S.nk, io = S.i_out[b];
+  const double z = S.zout[(long long)b * MAX_OUT + io], a = S.aout[(long long)b * MAX_OUT + io];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    double *h = S.hdr + ((long long)b * MAX_OUT + io) * 5;
+    const GrowthTab gt = growth_tab(S, b);
+    double D = NAN, dD = NAN;
+    growth_D_dD(gt, z, 1e-3, &D, &dD);  // hdr:964-965
+    h[0] = S.t[b];
+    h[1] = a;
+    h[2] = z;
+    h[3] = sqrt(bg_H2(c, a)) * H0H;
+    h[4] = D * D * c.sigv2_0;
+    if (io == 0) {
+      double D0 = NAN;
+      growth_D_dD(gt, 0.0, 1e-3, &D0, &dD);
+      S.hdr0[2 * b] = log(1.0 / c.a_in);  // rt:1598
+      S.hdr0[2 * b + 1] = D0 * D0 * c.sigv2_0;
+    }
+  }
+  if (i >= nk || i < S.k_lo || i >= S.k_hi) return;
+  const double k = kgrid[i];
+  const int ncols = S.ncols[b];
+  double *row = S.out + S.out_off[b] + ((long long)io * nk + i) * ncols;
+  const double *y = S.y + (long long)b * N_U * nk + i;
+  const double a_ain = a / c.a_in, a2 = a_ain * a_ain, a3 = a2 * a_ain, a4 = a2 * a2;
+  int col = 0;
+  row[col++] = k;
+  if (c.sw_pl) {
+    double D = NAN, dD = NAN;
+    const double Pcb = [&] {
+      // Plin_cb and D,dD share the look-ups
+      const double fn = c.On / c.Om, fc = 1.0 - fn;
+      const double T = S.Tgrid[(long long)b * nk + i];
+      const double B = ode_row_beta(S, b, i, a);
+      const double F = 1.0 - fn + B;
+      ode_row_D_dD(S, b, i, z, &D, &dD);
+      const double P = c.Norm * pow(k, c.ns) * T * T * F * F * D * D;
+      if (fn <= 1e-10) return P;
+      const double Rr = 1.0 / (fc + B);
+      return P * Rr * Rr;
+    }();
+    const double aL = a * 0.999, aR = fmin(1.0, a * 1.001);  // rt:1660-1661
+    const double B_eta = ode_row_beta(S, b, i, a), B1 = ode_row_beta(S, b, i, 1.0);
+    const double B_left = ode_row_beta(S, b, i, aL), B_right = ode_row_beta(S, b, i, aR);
+    const double dlnB = (c.fnu < 1e-10) ? 0.0 : (a / B_eta) * (B_right - B_left) / (aR - aL);
+    double Pnu = 0.0;
+    {
+      const double fn = c.On / c.Om, fc = 1.0 - fn;
+      if (fn > 1e-10) {
+        const double T = S.Tgrid[(long long)b * nk + i];
+        const double F = 1.0 - fn + B_eta;
+        const double P = c.Norm * pow(k, c.ns) * T * T * F * F * D * D;
+        const double Rr = B_eta / fn / (fc + B_eta);
+        Pnu = P * Rr * Rr;
+      }
+    }
+    row[col++] = D;
+    row[col++] = a * dD / D;
+    row[col++] = Pcb;
+    row[col++] = B_eta / (B1 + 1e-100);
+    row[col++] = dlnB;
+    row[col++] = Pnu;
+  }
+  row[col++] = exp(y[0]) * a2;
+  row[col++] = exp(y[(long long)nk]) * a2;
+  row[col++] = exp(y[2LL * nk]) * a2;
+  const bool have_int = (c.sw_nl && c.sw_1l);  // rt:1646; otherwise the reference prints
+                                               // uninitialised memory (zeros in its goldens)
+  const double *s1 = S.src + (long long)b * N_SRC * nk + i;
+  if (S.print_A)
+    for (int j = 0; j < N_UI; j++) row[col++] = have_int ? s1[(long long)j * nk] : 0.0;
+  if (S.print_I)
+    for (int j = 0; j < N_UI; j++) row[col++] = y[(long long)(N_UP + j) * nk];
+  if (c.sw_pr) {
+    double Q[N_UQ];
+    for (int j = 0; j < N_UQ; j++) Q[j] = y[(long long)(N_UP + N_UI + j) * nk];
+    const double pk = M_PI * k;
+    if (S.print_bias) {
+      row[col++] = pk * pbis_comb(Q, 2, 2) * a3;
+      row[col++] = pk * pbis_comb(Q, 2, 1) * a3;
+      row[col++] = pk * pbis_comb(Q, 4, 1) * a3;
+      row[col++] = pk * pbis_comb(Q, 4, 0) * a3;
+      row[col++] = pk * pbis_comb(Q, 6, 0) * a3;
+      for (int j = 0; j < 9; j++) row[col++] = have_int ? s1[(long long)(38 + j) * nk] * a4 : 0.0;
+      for (int j = 0; j < 8; j++) row[col++] = have_int ? s1[(long long)(47 + j) * nk] * a4 : 0.0;
+    } else {
+      row[col++] = (pk * pbis_comb(Q, 2, 2) + pk * pbis_comb(Q, 2, 1)) * a3;
+      row[col++] = (pk * pbis_comb(Q, 4, 1) + pk * pbis_comb(Q, 4, 0)) * a3;
+      row[col++] = pk * pbis_comb(Q, 6, 0) * a3;
+      double PT[4] = {0, 0, 0, 0};
+      if (have_int) {  // rt:1353-1358
+        PT[0] = s1[38LL * nk] + s1[39LL * nk] + s1[40LL * nk];
+        PT[1] = s1[41LL * nk] + s1[42LL * nk] + s1[43LL * nk];
+        PT[2] = s1[44LL * nk] + s1[45LL * nk];
+        PT[3] = s1[46LL * nk];
+      }
+      for (int j = 0; j < 4; j++) row[col++] = PT[j] * a4;
+    }
+  }
+  if (S.print_Q)
+    for (int j = 0; j < N_UQ; j++) row[col++] = y[(long long)(N_UP + N_UI + j) * nk] * a3;
+}
+
+// ---------------------------------------------------------------------------- launchers
+void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *dyv, int stage,
+                const int *mask, cudaStream_t st) {
+  const int nrows = S.k_hi - S.k_lo;
+  k_rhs<<<dim3((nrows + 127) / 128, S.B), 128, 0, st>>>(S, kgrid, yv, dyv, stage, mask);
+}
+void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st) {
+  const long long n = (long long)N_U * S.nk;
+  k_combine<<<dim3((unsigned)((n + 255) / 256), S.B), 256, 0, st>>>(S, stage, mask);
+}
+void launch_final(const Batch &S, const int *mask, cudaStream_t st) {
+  const long long n = (long long)N_U * S.nk;
+  k_final<<<dim3((unsigned)((n + 255) / 256), S.B), 256, 0, st>>>(S, mask);
+}
+void launch_ctrl_begin(const Batch &S, cudaStream_t st) { k_ctrl_begin<<<(S.B + 127) / 128, 128, 0, st>>>(S); }
+void launch_ctrl_end(const Batch &S, int max_attempts, cudaStream_t st) {
+  k_ctrl_end<<<(S.B + 127) / 128, 128, 0, st>>>(S, max_attempts);
+}
+void launch_accept(const Batch &S, cudaStream_t st) {
+  const long long n = (long long)N_U * S.nk;
+  k_accept<<<dim3((unsigned)((n + 255) / 256), S.B), 256, 0, st>>>(S);
+}
+void launch_output(const Batch &S, const double *kgrid, cudaStream_t st) {
+  k_output<<<dim3((S.nk + 127) / 128, S.B), 128, 0, st>>>(S, kgrid);
+}
+
+}  // namespace rtrg

@@ -1,0 +1,132 @@
+// Device-side data layout of one batch of cosmologies (all pointers are device pointers).
+//
+// HBM layout (doubles unless noted; B = cosmologies in the batch, nk output wavenumbers,
+// np = 4 nk padded grid, N_EQ = 41 nk):
+//   state vectors      y, ytmp, ynew, yerr, k[6]     [B][41][nk]   component-major like the
+//                                                    reference's y[c*nk+i] (rt:1418-1423)
+//   beta rows          bred   [B][n_zmax][nkk]       Beta_P pre-reduced in k at the nk grid
+//                                                    wavenumbers and the n_lnk+1 growth ones
+//   growth tables      G, dD  [B][n_lna+1][n_lnk+1]; Dnorm [B][n_lnk+1]
+//   growth rows        Grow, dDrow [B][n_lna+1][nk]; D0row [B][nk]
+//   integrals          Prev   [B][3][LP]             reversed, zero-padded P q^2 (TMA source)
+//                      P3     [B][3][np]             extrapolated, windowed spectra
+//                      Jpart  [B][14][nchunk][9][nk] partial bilinear sums
+//                      PZb    [B][7][3][nk]
+//                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
+//   weight tables      Tc     [14][NUp][ldT]         compact circulant kernels (L2 resident)
+#pragma once
+#include "rtrg_math.h"
+
+namespace rtrg {
+
+enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55 };
+#ifndef RTRG_NKERN_DEFINED
+#define RTRG_NKERN_DEFINED
+enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
+#endif
+enum { BIL_R = 8 };  // output rows per CTA of the bilinear kernel
+enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
+
+struct IntegralTabs {
+  int nk, np, nshift, jlo, nsup, nloMR;
+  int NV;      // nsup + BIL_R - 1 : lag range a row block touches
+  int NVp;     // NV rounded up to a multiple of BIL_R
+  int LP;      // padded length of one reversed spectrum (even)
+  int NUp;     // rows of the compact kernel table (>= nk + NVp)
+  int ldT;     // leading dimension of the compact kernel table
+  int nchunk;  // CTAs along the lag dimension
+  double dlnk;     // grid spacing in ln k
+  double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
+  const double *Tc;    // [14][NUp][ldT]  Tc[n][v''][u''] = T_n[u][v]
+  const double *Tlo;   // [nsup][nsup]    kernel 0 at the low-k row nloMR (reversed indices)
+  const double *kfac;  // [14][nk]
+  const double *G;     // [7][2np-1]
+  const double *WP;    // [np]
+  const double *kpad;  // [np]
+  const double *kgrid; // [nk]
+  // extrapolation stencil of Pab (rt:181-232) for every padded sample
+  const int *ex_n0;       // [np] first node of the 4-point stencil
+  const double *ex_w;     // [np][4]
+  const double *ex_dx;    // [np] lnk - lnk[nk-1] for the power-law extrapolation, else 0
+  // assembly table (sorted by output row)
+  int n_terms;
+  const int *t_start;     // [56]
+  const short *t_src, *t_index, *t_kpow;
+  const double *t_coef;
+};
+
+struct Batch {
+  int B, nk, np, n_lna, n_lnk, nkk, n_zmax;
+  double eps_abs, eps_rel, z1l, beta_kmin, beta_kmax, a_early;
+  int print_A, print_I, print_Q, print_bias;
+  int k_lo, k_hi;  // k-rows owned by this rank (k-sharding); [0,nk) otherwise
+  Cosmo *cosmo;            // [B]
+  double *zout, *aout, *etaout;  // [B][MAX_OUT] output redshifts, 1/(1+z), ln(a/a_in)
+  // pooled input tables
+  const double *lnkT, *lnT, *anodes, *kb, *beta;
+  // linear-theory work
+  double *bred;            // [B][n_zmax][nkk]
+  const double *lna, *lnkg;// [n_lna+1], [n_lnk+1]
+  double *G, *dD, *Dnorm;
+  double *Grow, *dDrow, *D0row;
+  double *Tgrid;           // [B][nk] transfer function at the grid wavenumbers
+  // 1-loop cache at z1l (rt:1291-1313)
+  double *src_z1l;         // [B][55][nk]
+  double *D_z1l;           // [B][nk]
+  double *y_z1l;           // [B][3][nk] ln P_lin,cb(z1l) three times (rt:1299-1306)
+  // ODE state
+  double *y, *ytmp, *ynew, *yerr, *kst;   // kst: [6][B][41][nk]
+  double *src;             // [B][55][nk]  sources of the current RHS evaluation
+  // integral work space
+  double *Prev, *P3, *Jpart, *PZb, *Jlo;
+  // stepper control (per cosmology)
+  double *t, *h, *h_try;   // current eta, suggested step, step of this attempt
+  unsigned long long *rmax_bits;
+  int *i_out, *flag_out, *flag_step, *flag_acc, *final_step, *done;
+  int *m_full_step, *m_full_acc, *m_out_int;  // masks of the integral launches
+  long long *counters;     // [B][4]
+  int *n_active;           // [1]
+  // outputs
+  double *out;             // concatenated tables
+  long long *out_off;      // [B] offset of cosmology b in out
+  int *ncols;              // [B]
+  double *hdr;             // [B][MAX_OUT][5]
+  double *hdr0;            // [B][2]
+};
+
+RT_HD BetaTab beta_tab(const Batch &S, const Cosmo &c) {
+  BetaTab t;
+  t.n_z = c.n_z;
+  t.n_kb = c.n_kb;
+  t.a = S.anodes + c.offA;
+  t.k = S.kb + c.offKb;
+  t.beta = S.beta + c.offB;
+  t.fn = c.On / c.Om;
+  t.kmin = S.beta_kmin;
+  t.kmax = S.beta_kmax;
+  return t;
+}
+RT_HD GrowthTab growth_tab(const Batch &S, int b) {
+  GrowthTab g;
+  g.n_lna = S.n_lna;
+  g.n_lnk = S.n_lnk;
+  g.lna = S.lna;
+  g.lnk = S.lnkg;
+  const long long n = (long long)(S.n_lna + 1) * (S.n_lnk + 1);
+  g.G = S.G + b * n;
+  g.dD = S.dD + b * n;
+  g.Dnorm = S.Dnorm + (long long)b * (S.n_lnk + 1);
+  return g;
+}
+RT_HD LinCtx lin_ctx(const Batch &S, int b) {
+  LinCtx L;
+  L.c = &S.cosmo[b];
+  L.bt = beta_tab(S, S.cosmo[b]);
+  L.gt = growth_tab(S, b);
+  L.lnkT = S.lnkT + S.cosmo[b].offT;
+  L.lnT = S.lnT + S.cosmo[b].offT;
+  L.nT = S.cosmo[b].nT;
+  return L;
+}
+
+}  // namespace rtrg

@@ -149,38 +149,11 @@ RT_HD double cub4(const double *x, double f0, double f1, double f2, double f3, d
          (xq - x[0]) * (xq - x[1]) * (xq - x[3]) / (x[2] - x[0]) / (x[2] - x[1]) / (x[2] - x[3]) * f2 +
          (xq - x[0]) * (xq - x[1]) * (xq - x[2]) / (x[3] - x[0]) / (x[3] - x[1]) / (x[3] - x[2]) * f3;
 }
-// 4 interpolation weights on nodes x[n0..n0+3] such that f(xq) = sum w_m f[n0+m]; encodes
-// the reference's rule "cubic inside, linear (extrapolating) in the first/last interval".
-// `two_d` selects the 2-D variant of the edge rule (tab:281-321: linear when n==0 or
-// n==size-2, cubic for 0<n<size-2) which coincides with the 1-D rule (tab:250-260).
+// interpolation weights on 4 consecutive nodes n0..n0+3: f(xq) = sum_m w[m] f[n0+m]
 struct Stencil {
   int n0;
   double w[4];
 };
-RT_HD Stencil tab_stencil(const double *x, int size, double xq) {
-  Stencil s;
-  const int n = tab_find(x, size, xq);
-  if (n <= 0 || n >= size - 2) {
-    const int m = (n <= 0) ? 0 : size - 2;
-    // place the two linear weights inside a 4-wide window that stays in range
-    int n0 = m - 1;
-    if (n0 < 0) n0 = 0;
-    if (n0 > size - 4) n0 = size - 4 < 0 ? 0 : size - 4;
-    s.n0 = n0;
-    s.w[0] = s.w[1] = s.w[2] = s.w[3] = 0;
-    const double t = (xq - x[m]) / (x[m + 1] - x[m]);
-    s.w[m - n0] = 1.0 - t;
-    s.w[m + 1 - n0] = t;
-  } else {
-    const double *p = x + n - 1;
-    s.n0 = n - 1;
-    s.w[0] = (xq - p[1]) * (xq - p[2]) * (xq - p[3]) / (p[0] - p[1]) / (p[0] - p[2]) / (p[0] - p[3]);
-    s.w[1] = (xq - p[0]) * (xq - p[2]) * (xq - p[3]) / (p[1] - p[0]) / (p[1] - p[2]) / (p[1] - p[3]);
-    s.w[2] = (xq - p[0]) * (xq - p[1]) * (xq - p[3]) / (p[2] - p[0]) / (p[2] - p[1]) / (p[2] - p[3]);
-    s.w[3] = (xq - p[0]) * (xq - p[1]) * (xq - p[2]) / (p[3] - p[0]) / (p[3] - p[1]) / (p[3] - p[2]);
-  }
-  return s;
-}
 RT_HD double stencil_apply(const Stencil &s, const double *f, int stride = 1) {
   double r = 0;
   for (int m = 0; m < 4; m++)
@@ -217,10 +190,11 @@ RT_HD double tab2d(const double *xs, int X, const double *ys, int Y, const doubl
   return lin2(ys[ny], ys[ny + 1], fy[1], fy[2], yq);
 }
 // x-direction rule of the 2-D table applied to one pre-reduced row g[0..X)
-RT_HD double tab_row_x(const double *xs, int X, const double *g, double xq) {
+RT_HD double tab_row_x(const double *xs, int X, const double *g, double xq, long long gs = 1) {
   const int nx = tab_find(xs, X, xq);
-  if (nx > 0 && nx < X - 2) return cub4(xs + nx - 1, g[nx - 1], g[nx], g[nx + 1], g[nx + 2], xq);
-  return lin2(xs[nx], xs[nx + 1], g[nx], g[nx + 1], xq);
+  if (nx > 0 && nx < X - 2)
+    return cub4(xs + nx - 1, g[(nx - 1) * gs], g[nx * gs], g[(nx + 1) * gs], g[(nx + 2) * gs], xq);
+  return lin2(xs[nx], xs[nx + 1], g[nx * gs], g[(nx + 1) * gs], xq);
 }
 // y-direction weights of the 2-D table (rows ny-1..ny+2; linear at the two edge intervals)
 RT_HD Stencil tab_stencil_y(const double *ys, int Y, double yq) {
@@ -264,12 +238,12 @@ RT_HD double beta_P(const BetaTab &t, double a, double k) {
   return tab2d(t.a, t.n_z, t.k, t.n_kb, t.beta, a, k);
 }
 // the same look-up through a row pre-reduced in k: brow[j] = sum_r wy_r beta[j][ny-1+r]
-RT_HD double beta_row(const BetaTab &t, const double *brow, double a) {
+RT_HD double beta_row(const BetaTab &t, const double *brow, double a, long long bs = 1) {
   if (t.n_z == 0) return 0;
   if (t.fn < 1e-10) return 0;
   if (a > 1.001) return NAN;
   if (a > 1.0) a = 1.0;
-  return tab_row_x(t.a, t.n_z, brow, a);
+  return tab_row_x(t.a, t.n_z, brow, a, bs);
 }
 
 // ------------------------------------------------------------------------------------
@@ -373,21 +347,39 @@ struct GrowthCtx {
   BgStatic bg;
   BetaTab bt;
   const double *brow;  // beta row pre-reduced at this wavenumber (clamped k)
+  long long bstride;   // stride between successive a-nodes of brow
 };
 RT_HD void growth_rhs(const GrowthCtx &g, double a, const double y[2], double f[2]) {
   const double F0 = 1.5 * g.bg.Om / (pow(a, 5.0) * bgs_H2(g.bg, a));
   const double F1 = (3.0 + bgs_dlnH(g.bg, a)) / a;
-  const double beta = (a < 1e-3) ? g.bg.fn : beta_row(g.bt, g.brow, fmin(a, 1.0));
+  const double beta = (a < 1e-3) ? g.bg.fn : beta_row(g.bt, g.brow, fmin(a, 1.0), g.bstride);
   f[0] = y[1];
   f[1] = -F1 * y[1] + F0 * (g.bg.fc + beta) * y[0];  // F_MG = 0 (hdr:151-153)
 }
 
-// one leg a_begin -> a_end (hdr:170-190); returns number of attempted steps
-RT_HD int growth_integrate(const GrowthCtx &g, double a_begin, double a_end, double y[2]) {
+struct PDTableau {
+  double A[13][12], C[13], B8[13], B7[13];
+};
+inline PDTableau make_pd_tableau() {
   const double A[13][12] = {RT_PD_ROWS};
   const double C[13] = {RT_PD_C};
   const double B8[13] = {RT_PD_B8};
   const double B7[13] = {RT_PD_B7};
+  PDTableau T;
+  for (int i = 0; i < 13; i++) {
+    for (int j = 0; j < 12; j++) T.A[i][j] = A[i][j];
+    T.C[i] = C[i];
+    T.B8[i] = B8[i];
+    T.B7[i] = B7[i];
+  }
+  return T;
+}
+
+// one leg a_begin -> a_end (hdr:170-190); returns number of attempted steps
+RT_HD int growth_integrate(const PDTableau &PD, const GrowthCtx &g, double a_begin, double a_end,
+                           double y[2]) {
+  const double(*A)[12] = PD.A;
+  const double *C = PD.C, *B8 = PD.B8, *B7 = PD.B7;
   double t = a_begin;
   const double t1 = a_end;
   double h = 1e-6 * t;
@@ -484,12 +476,12 @@ RT_HD bool growth_D_dD(const GrowthTab &t, double z, double k, double *D, double
 }
 // the same through rows pre-reduced at a fixed wavenumber: Grow[i], dDrow[i], i<=n_lna
 RT_HD bool growth_D_dD_row(const double *lna, int n_lna, const double *Grow, const double *dDrow,
-                           double D0, double z, double *D, double *dDda) {
+                           long long rs, double D0, double z, double *D, double *dDda) {
   const double a = 1.0 / (z + 1.0);
   if (a > GROWTH_A_MAX || a < GROWTH_A_MIN) return false;
   const double lna0 = log(a);
-  *D = tab_row_x(lna, n_lna + 1, Grow, lna0) * a / D0;
-  *dDda = tab_row_x(lna, n_lna + 1, dDrow, lna0) / D0;
+  *D = tab_row_x(lna, n_lna + 1, Grow, lna0, rs) * a / D0;
+  *dDda = tab_row_x(lna, n_lna + 1, dDrow, lna0, rs) / D0;
   return true;
 }
 
