@@ -1,0 +1,96 @@
+"""End-to-end parity: examples/1_redTime through the batched device stepper vs
+  (a) the reference's own golden example_redTime_result.dat (genuine GSL), and
+  (b) the ORACLE output (unmodified reference + mini-GSL shim), 1-loop and full Time-RG.
+Tolerance (north star): max relative error <= 1e-6 in columns 1-7 and <= 1e-5 in columns
+8-17; columns 11-17 of the lowest k rows carry the reference's own FFT round-off (SURVEY H2,
+V13), so there the bound is 1e-5 |ref| + floor(k, col) with the floor measured between the
+genuine-GSL golden and the oracle."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import redtime_b200 as rt
+from conftest import GOLDEN, parse_tables
+
+pytestmark = pytest.mark.gpu
+NK = 128
+
+
+def load_oracle(tag):
+    with gzip.open(os.path.join(GOLDEN, "example1_oracle_%s.dat.gz" % tag), "rt") as f:
+        return parse_tables(f.read())
+
+
+def run(dirname, **cfg):
+    h = rt.RedTimeB200(**cfg)
+    h.add_cosmology(rt.read_run_dir(dirname))
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    cnt = h.counters(0)
+    h.close()
+    return tables[0], hdr[0], hdr0[0], status[0], cnt
+
+
+def col_err(got, ref):
+    return np.max(np.abs(got - ref) / (np.abs(ref) + 1e-300), axis=(0, 1))
+
+
+def test_example1_1loop(example1_dir, golden_example1):
+    tab, hdr, hdr0, status, cnt = run(example1_dir)
+    assert status == 0
+    _, gold = golden_example1
+    gold = gold.reshape(7, NK, 17)
+    _, orc = load_oracle("1loop")
+    orc = orc.reshape(7, NK, 17)
+    assert tab.shape == (7, NK, 17)
+    # the step sequence genuine GSL took
+    assert (cnt["attempts"], cnt["rejected"]) == (23, 4)
+    for ref in (gold, orc):
+        e = col_err(tab, ref)
+        assert np.all(e[:7] < 1e-6), e
+        assert np.all(e[7:10] < 1e-5), e
+        hi = ref[0, :, 0] > 5.7e-3
+        assert np.all(col_err(tab[:, hi], ref[:, hi])[10:] < 1e-5), e
+    # low-k rows of columns 11-17: not noisier than genuine GSL vs the oracle
+    floor = np.abs(gold - orc)
+    assert np.all(np.abs(tab - orc)[:, :, 10:] <= 1e-5 * np.abs(orc[:, :, 10:]) + 4 * floor[:, :, 10:] + 1e-300)
+
+
+def test_example1_header_lines(example1_dir, golden_example1, tmp_path):
+    tab, hdr, hdr0, status, cnt = run(example1_dir)
+    p = str(tmp_path / "out.dat")
+    rt.print_result(p, NK, tab, hdr, hdr0)
+    mine = [l for l in open(p).read().split("\n") if l.startswith("#")]
+    ref, _ = golden_example1
+    assert mine == ref  # banner, eta_fin/sigmaV2 line and the 7 per-output lines, byte-identical
+
+
+def test_example1_full_trg(example1_full_dir):
+    tab, hdr, hdr0, status, cnt = run(example1_full_dir)
+    assert status == 0
+    _, orc = load_oracle("full")
+    orc = orc.reshape(7, NK, 17)
+    e = col_err(tab, orc)
+    assert np.all(e[:7] < 1e-6), e
+    assert np.all(e[7:10] < 1e-5), e
+    hi = orc[0, :, 0] > 5.7e-3
+    assert np.all(col_err(tab[:, hi, :13], orc[:, hi, :13])[10:] < 1e-5), e
+    assert not tab[:, :, 13:].any()  # columns 14-17 are zeros in full-TRG mode
+
+
+def test_batch_of_identical_and_mixed_cosmologies(example1_dir, example1_full_dir):
+    """Batching must not change any result: [1-loop, full, 1-loop] in one handle."""
+    single, *_ = run(example1_dir)
+    h = rt.RedTimeB200()
+    h.add_cosmology(rt.read_run_dir(example1_dir))
+    h.add_cosmology(rt.read_run_dir(example1_full_dir))
+    h.add_cosmology(rt.read_run_dir(example1_dir))
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    assert not status.any()
+    assert np.array_equal(tables[0], single) and np.array_equal(tables[2], single)
+    _, orc = load_oracle("full")
+    assert np.all(col_err(tables[1][:, :, :10], orc.reshape(7, NK, 17)[:, :, :10]) < 1e-5)
+    h.close()
