@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- cosmology*redshift outputs per second of the Time-RG hot path at nk=128.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              this library on N B200s
+  python bench.py --impl reference [--gpus N] [--steps K] ...      the reference on host cores
+
+A "step" is one pass of the whole hot path over one batch of synthetic cosmologies per GPU
+(device-side linear theory tables + sigma_8 normalisation + 1-loop mode-coupling integrals +
+Time-RG evolution with the batched RKF45 stepper + output tables at 8 redshifts).
+
+  value : outputs/s with the inputs already resident in HBM (CUDA events on the library's
+          stream, max over ranks); work of all ranks / that time ("weak" scaling: every rank
+          owns its own --cosmologies batch, no data-path collective).
+  e2e   : the same through the reference-facing C-ABI with HOST buffers: rtrg_add_cosmology
+          (host) -> rtrg_prepare (H2D + device init) -> rtrg_run (evolution + D2H of the tables).
+  roofline     : the dominant kernel (k_bilinear, FP64 FMA pipe): algorithmic FLOP of all its
+                 launches / its CUDA-event time, against the DFMA peak measured live.
+  cpu_baseline : oracle/_ref/redTime (the UNMODIFIED reference sources + mini-GSL shim) as one
+                 single-thread process per host core on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cosmology*redshift outputs/sec at nk=128"
+UNIT = "outputs/s"
+NK = 128
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cosmologies", type=int, default=1024, help="cosmologies per GPU and step")
+    ap.add_argument("--mode", default="1loop", choices=["1loop", "full"],
+                    help="1loop = switches 1 1 1 1 (headline); full = 1 0 1 1 (full Time-RG)")
+    ap.add_argument("--subsample", type=int, default=1, help="keep every n-th CAMB table row")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: concurrent processes (0 = host cores)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    sw = "1 1 1 1 (1-loop)" if a.mode == "1loop" else "1 0 1 1 (full Time-RG)"
+    return ("throughput sweep (BASELINE configs[4]): %d w0wa+massive-nu cosmologies per GPU x 8 redshifts, "
+            "nk=128, switches %s, example-1 CAMB tables (%d rows x 12 redshifts) with per-cosmology tilt, "
+            "Latin-hypercube parameters seed 20261018" % (a.cosmologies, sw, -(-15447 // a.subsample)))
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference binary on the host cores
+# ------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "redTime")
+    return p if os.path.exists(p) else None
+
+
+def reference_step(dirs, binary):
+    """One process per run directory, one OpenMP thread each, pinned round-robin to the
+    allowed cores; returns wall seconds from first spawn to last exit."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "1"
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = list(range(os.cpu_count() or 1))
+    use_taskset = shutil.which("taskset") is not None
+    t0 = time.perf_counter()
+    procs = []
+    for i, d in enumerate(dirs):
+        cmd = [binary]
+        if use_taskset:
+            cmd = ["taskset", "-c", str(cores[i % len(cores)])] + cmd
+        procs.append(subprocess.Popen(cmd, cwd=d, env=env, stdout=open(os.path.join(d, "out.dat"), "w"),
+                                      stderr=subprocess.DEVNULL))
+    rcs = [p.wait() for p in procs]
+    wall = time.perf_counter() - t0
+    if any(rcs):
+        raise RuntimeError("reference process failed: %s" % rcs)
+    return wall
+
+
+def reference_setup(a, nproc, tmp):
+    from redtime_b200 import workload as wl
+    base = wl.load_example1(a.subsample)
+    sw = (1, 1, 1, 1) if a.mode == "1loop" else (1, 0, 1, 1)
+    cosmos = wl.make_cosmologies(nproc, base, seed=wl.SEED, switches=sw)
+    return [wl.write_run_dir(os.path.join(tmp, "c%04d" % i), c) for i, c in enumerate(cosmos)]
+
+
+def run_reference_arm(a, rank):
+    if rank != 0:
+        return
+    steps = a.steps if a.steps is not None else 2
+    warm = a.warmup if a.warmup is not None else 1
+    binary = reference_binary()
+    if binary is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/redTime not built (make -C oracle)"}))
+        return
+    nproc = a.ref_procs or host_cores()
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = reference_setup(a, nproc, tmp)
+        for _ in range(warm):
+            reference_step(dirs, binary)
+        t = [reference_step(dirs, binary) for _ in range(steps)]
+    n_out = len(REDSHIFTS())
+    wall = float(np.sum(t))
+    value = steps * nproc * n_out / wall
+    sample = "%d cosmologies x %d redshifts per step, one single-thread process per core" % (nproc, n_out)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def REDSHIFTS():
+    from redtime_b200 import workload as wl
+    return wl.REDSHIFTS_CE
+
+
+def cpu_baseline(a):
+    """Bounded sample for the default bench line: ONE step of the reference arm."""
+    binary = reference_binary()
+    if binary is None:
+        return None
+    nproc = host_cores()
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = reference_setup(a, nproc, tmp)
+        wall = reference_step(dirs, binary)
+    n_out = len(REDSHIFTS())
+    return {"value": nproc * n_out / wall, "unit": UNIT, "cores": nproc, "kind": "reference",
+            "sample": "%d cosmologies x %d redshifts (one single-thread oracle/_ref/redTime process per core), "
+                      "%.1f s wall" % (nproc, n_out, wall)}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# this library
+# ------------------------------------------------------------------------------------------
+def flops_per_integral_eval(grid, with_jn0, nk):
+    """Algorithmic FLOP of ONE evaluation of the mode-coupling integrals for one cosmology in
+    the factored form the kernel uses: per bilinear kernel n, for each of the nk
+    rows and 3 beta-side spectra an nsup x nsup matrix-vector product (2 nsup^2 FLOP), then 9
+    alpha-side dot products (2 nsup)."""
+    nsup = grid["nsup"]
+    nkern = 14 if with_jn0 else 7
+    return nkern * nk * (3 * 2.0 * nsup * nsup + 9 * 2.0 * nsup)
+
+
+def run_b200(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import redtime_b200 as rt
+    from redtime_b200 import workload as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; redtime_b200 has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    steps = a.steps if a.steps is not None else 5
+    warm = max(a.warmup if a.warmup is not None else 3, 0)
+
+    B = a.cosmologies
+    base = wl.load_example1(a.subsample)
+    sw = (1, 1, 1, 1) if a.mode == "1loop" else (1, 0, 1, 1)
+    cosmos = wl.make_cosmologies(B, base, seed=wl.SEED + 7919 * rank, switches=sw)
+    n_out = len(wl.REDSHIFTS_CE)
+    outputs_per_step = B * n_out
+
+    h = rt.RedTimeB200(device=local_rank, nk=NK)
+    stream = torch.cuda.Stream()
+    h.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def upload():
+        h.clear()
+        for c in cosmos:
+            h.add_cosmology(c)
+        h.prepare()
+
+    def e2e_step():
+        upload()
+        return h.run()
+
+    def resident_step():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        h.device_init()
+        return h.run_resident()
+
+    # ---- resident-input timing ("value")
+    upload()
+    for _ in range(warm):
+        st = resident_step()
+    if warm and st.any():
+        print("bench.py: warning: %d cosmologies failed (status != 0)" % int(np.count_nonzero(st)), file=sys.stderr)
+    clocks = ClockSampler(local_rank)
+    h.set_profiling(True)
+    l0 = h.launch_count()
+    sync_all()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        resident_step()
+    ev1.record(stream)
+    sync_all()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = reduce_max(ev0.elapsed_time(ev1))
+    launches = h.launch_count() - l0
+    prof = h.profile()
+    h.set_profiling(False)
+    evals = sum(h.counters(i)["integral_evals"] for i in range(B))  # per step (last run)
+    value = world * outputs_per_step * steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(min(warm, 1)):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tables, hdr, hdr0, status = e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = reduce_max(time.perf_counter() - t0)
+        h2d = sum(c["k_T"].nbytes * 2 + c["k_b"].nbytes + c["Tc_b"].nbytes + c["z_interp"].nbytes for c in cosmos)
+        h2d += B * (9 * 8 + 64 * 8 * 3)
+        d2h = sum(t.nbytes for t in tables) + hdr.nbytes + hdr0.nbytes
+        e2e = {"value": world * outputs_per_step * steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * t_e2e / steps, "timing": "wall clock around the C-ABI calls, max over ranks"}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel
+    grid = rt.grid_info(NK)
+    n_bil, ms_bil = prof["k_bilinear"]
+    flop_eval = flops_per_integral_eval(grid, True, NK)
+    flop_total = flop_eval * evals * steps
+    peak = rt.dfma_peak_tflops(local_rank, 0.5)
+    achieved = flop_total / (ms_bil * 1e-3) * 1e-12 if ms_bil > 0 else 0.0
+    sm_clk = 1.965e9
+    roof = {"bound": "fp64", "kernel": "k_bilinear", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak else None, "traffic": None,
+            "peak_source": "DFMA loop measured live by rtrg_bench_dfma (MEASURED_PEAKS.json has no FP64 figure); "
+                           "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = %.1f TFLOP/s" % (148 * 64 * 2 * sm_clk * 1e-12),
+            "launches": n_bil, "avg_launch_ms": ms_bil / max(n_bil, 1),
+            "algorithmic_flop_per_integral_evaluation": flop_eval, "integral_evaluations_per_step": evals,
+            "share_of_step": ms_bil / ms_total}
+    kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in prof.items() if v[0]}
+    cpu = None if a.no_cpu_baseline else cpu_baseline(a)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "cosmologies_per_gpu": B, "redshifts": n_out, "nk": NK,
+                       "mode": a.mode, "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2"
+                       % (sum(c["Tc_b"].nbytes * 2 for c in cosmos) / 1e9)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "kernel_ms_in_timed_region": kernels}
+    print(json.dumps(line))
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank)
+        return
+    if world == 1 and a.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517"] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_b200(a, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

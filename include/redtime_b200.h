@@ -98,13 +98,17 @@ int rtrg_num_columns(const rtrg_handle *h, int icosmo);
  * conditions, 1-loop cache.  Replaces src/redTime.cc:1559-1586 +
  * src/AU_cosmological_parameters.h:513-971 first-call initialisations. */
 int rtrg_prepare(rtrg_handle *h);
+/* Device-side part of rtrg_prepare() alone, on the inputs already resident in HBM (no
+ * host->device traffic): used to time the hot path with resident inputs. */
+int rtrg_device_init(rtrg_handle *h);
 
 /* The whole job (src/redTime.cc:1588-1742): evolve every cosmology with the
  * device-resident RKF45 stepper and write the output tables.
  *   out   : concatenated per cosmology, [n_out][nk][ncols] each (row-major)
  *   hdr   : [n_cosmo][RTRG_MAX_OUT][5] = eta, a, z, H, sigma_v^2 per output
  *   hdr0  : [n_cosmo][2] = eta_fin, sigmaV2(z=0)
- *   status: [n_cosmo] 0 = ok (may be NULL)                                          */
+ *   status: [n_cosmo] 0 = ok (may be NULL)
+ * out / hdr / hdr0 may be NULL: the tables then stay on the device (no D2H copy).     */
 int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *hdr0,
              int *status);
 /* Work counters of the last rtrg_run for cosmology i:
@@ -112,6 +116,16 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
 int rtrg_counters(const rtrg_handle *h, int icosmo, long long counters[4]);
 /* number of kernel launches issued by this handle so far */
 long long rtrg_launch_count(const rtrg_handle *h);
+/* Per-kernel device timing (CUDA events on the launching stream), off by default.
+ * Switching it on or off zeroes the totals.  Categories 0..rtrg_profile_categories()-1. */
+int rtrg_set_profiling(rtrg_handle *h, int on);
+int rtrg_profile_categories(void);
+const char *rtrg_profile_name(int cat);
+int rtrg_profile_query(const rtrg_handle *h, int cat, long long *n_launches, double *total_ms);
+
+/* FP64 FMA pipe peak of `device` in TFLOP/s (register-resident DFMA loop, best launch over
+ * about `seconds` of device time): the roofline denominator of the integral kernels.    */
+int rtrg_bench_dfma(int device, double seconds, double *tflops);
 
 /* ---- stage-level hooks with the reference's array layouts (parity tests) ---------- */
 /* src/redTime.cc:772-778: y[0..3nk) -> P[3][np] extrapolated and windowed            */

@@ -64,6 +64,12 @@ def load_library():
     lib.rtrg_num_cosmologies.argtypes = [C.c_void_p]
     lib.rtrg_num_columns.argtypes = [C.c_void_p, C.c_int]
     lib.rtrg_prepare.argtypes = [C.c_void_p]
+    lib.rtrg_device_init.argtypes = [C.c_void_p]
+    lib.rtrg_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.rtrg_profile_name.argtypes = [C.c_int]
+    lib.rtrg_profile_name.restype = C.c_char_p
+    lib.rtrg_profile_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _dp]
+    lib.rtrg_bench_dfma.argtypes = [C.c_int, C.c_double, _dp]
     lib.rtrg_run.argtypes = [C.c_void_p, _dp, C.c_size_t, _dp, _dp, _ip]
     lib.rtrg_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     lib.rtrg_extrap_P.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -186,6 +192,14 @@ def print_result(path, nk, out, hdr, hdr0, paramfile="params_redTime.dat"):
         libc.fclose(f)
 
 
+def dfma_peak_tflops(device=0, seconds=0.5):
+    """Measured FP64 FMA peak of the device (TFLOP/s)."""
+    lib = load_library()
+    t = C.c_double()
+    _check(lib.rtrg_bench_dfma(int(device), float(seconds), C.byref(t)))
+    return t.value
+
+
 class RedTimeB200:
     """One handle = one GPU + one (nk,kmin,kmax) grid; cosmologies are batched."""
 
@@ -247,6 +261,28 @@ class RedTimeB200:
 
     def prepare(self):
         _check(self.lib.rtrg_prepare(self.h))
+
+    def device_init(self):
+        """Device-side initialisation alone, on inputs already resident in HBM."""
+        _check(self.lib.rtrg_device_init(self.h))
+
+    def run_resident(self):
+        """Evolve all cosmologies; tables stay on the device (no D2H).  Returns status[]."""
+        status = np.zeros(self.n_cosmo, np.int32)
+        _check(self.lib.rtrg_run(self.h, None, 0, None, None, status.ctypes.data_as(_ip)))
+        return status
+
+    def set_profiling(self, on=True):
+        _check(self.lib.rtrg_set_profiling(self.h, int(on)))
+
+    def profile(self):
+        """{kernel name: (launches, total device ms)} since profiling was switched on."""
+        out = {}
+        for cat in range(self.lib.rtrg_profile_categories()):
+            n, ms = C.c_longlong(), C.c_double()
+            self.lib.rtrg_profile_query(self.h, cat, C.byref(n), C.byref(ms))
+            out[self.lib.rtrg_profile_name(cat).decode()] = (int(n.value), float(ms.value))
+        return out
 
     def run(self, raise_on_ode_failure=True):
         """Returns (tables, hdr, hdr0, status): tables[i] has shape [n_out_i, nk, ncols_i]."""

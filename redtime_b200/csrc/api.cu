@@ -20,13 +20,13 @@ namespace rtrg {
 // kernels_integrals.cu
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
-                     cudaStream_t st);
+                     cudaStream_t st, Profiler *prof);
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st);
 int integrals_configure();
 // kernels_linear.cu
 int linear_upload_constants();
-int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st);
+int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof);
 void launch_hook_DdD(const Batch &S, int b, double z, const double *k, int n, double *D, double *dD,
                      int *err, cudaStream_t st);
 void launch_hook_beta(const Batch &S, int b, double a, const double *k, int n, double *beta, int *err,
@@ -79,7 +79,7 @@ struct rtrg_handle {
   std::vector<double> kgrid;
   std::vector<HostCosmo> cos;
   Batch S;
-  bool prepared = false;
+  bool prepared = false, uploaded = false;
   long long launches = 0;
   std::vector<long long> out_off, counters;
   std::vector<int> ncols;
@@ -88,7 +88,34 @@ struct rtrg_handle {
   double *d_yinit = nullptr, *d_raw = nullptr, *d_scratch = nullptr;
   int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
   size_t scratch_len = 0;
+  Profiler profiler;
+  Profiler *prof = nullptr;  // &profiler when profiling is switched on
+  double prof_ms[PC_NCAT] = {0};
+  long long prof_n[PC_NCAT] = {0};
 };
+
+// timed launch of one of the ODE-side kernels
+#define ODE_LAUNCH(cat, call)        \
+  do {                               \
+    RT_TIC(h->prof, cat, st);        \
+    call;                            \
+    RT_TOC(h->prof, st);             \
+    h->launches++;                   \
+  } while (0)
+
+// fold the recorded events into the per-category totals (stream must be idle)
+static void prof_collect(rtrg_handle *h) {
+  if (!h->prof) return;
+  for (const Profiler::Rec &r : h->profiler.recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      h->prof_ms[r.cat] += ms;
+      h->prof_n[r.cat]++;
+    }
+  }
+  cudaGetLastError();
+  h->profiler.reset();
+}
 
 template <class T>
 static int dev_alloc(std::vector<void *> &pool, T **p, size_t n, bool zero = true) {
@@ -342,7 +369,7 @@ int rtrg_set_stream(rtrg_handle *h, void *cuda_stream) {
 int rtrg_clear_cosmologies(rtrg_handle *h) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   h->cos.clear();
-  h->prepared = false;
+  h->prepared = h->uploaded = false;
   return RTRG_OK;
 }
 
@@ -394,7 +421,7 @@ int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) {
     for (size_t i = 0; i < hc.beta.size(); i++) hc.beta[i] = fn * in->Tnu_b[i] / in->Tc_b[i];
   }
   h->cos.push_back(std::move(hc));
-  h->prepared = false;
+  h->prepared = h->uploaded = false;
   return RTRG_OK;
 }
 
@@ -403,7 +430,7 @@ int rtrg_prepare(rtrg_handle *h) {
   if (h->cos.empty()) return fail(RTRG_EINVAL, "no cosmologies");
   CU(cudaSetDevice(h->cfg.device));
   free_pool(h->batch_allocs);
-  h->prepared = false;
+  h->prepared = h->uploaded = false;
   const rtrg_config &cfg = h->cfg;
   const int B = (int)h->cos.size(), nk = cfg.nk, np = 4 * nk;
   Batch &S = h->S;
@@ -539,20 +566,36 @@ int rtrg_prepare(rtrg_handle *h) {
     return rc;
   }
 
+  h->uploaded = true;
+  return rtrg_device_init(h);
+}
+
+int rtrg_device_init(rtrg_handle *h) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (!h->uploaded) return fail(RTRG_EINVAL, "rtrg_prepare() has not uploaded any cosmology");
+  CU(cudaSetDevice(h->cfg.device));
+  h->prepared = false;
+  const rtrg_config &cfg = h->cfg;
+  Batch &S = h->S;
+  const IntegralTabs &tb = h->tb;
+  const int B = S.B, nk = S.nk;
+  const size_t NE = (size_t)B * N_U * nk;
   cudaStream_t st = h->stream;
-  h->launches += launch_linear_init(S, h->d_kgrid, st);
+  h->launches += launch_linear_init(S, h->d_kgrid, st, h->prof);
   CU(cudaMemcpyAsync(h->d_yinit, S.y, NE * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (h->any_1loop) {
     // 1-loop cache: the integrals of the linear spectrum at z1l (rt:1295-1313)
     std::vector<int> m(B);
-    for (int b = 0; b < B; b++) m[b] = cs[b].sw_nl && cs[b].sw_1l;
+    for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
     h->launches += launch_integrals(tb, S, S.y_z1l, 3LL * nk, S.src_z1l, nullptr, h->d_minit, h->any_pr,
-                                    cfg.print_bias, st);
+                                    cfg.print_bias, st, h->prof);
   }
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
+  prof_collect(h);
   // status of the device-side initialisation
+  std::vector<Cosmo> cs(B);
   CU(cudaMemcpy(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost));
   for (int b = 0; b < B; b++) h->cos[b].c.Norm = cs[b].Norm, h->cos[b].c.sigv2_0 = cs[b].sigv2_0, h->cos[b].c.status = cs[b].status;
   h->prepared = true;
@@ -587,30 +630,30 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     std::vector<int> m(B);
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, h->any_pr, 0, st);
+    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, h->any_pr, 0, st, h->prof);
   }
-  launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st), h->launches++;
+  ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st));
 
   int n_active = B;
   long long rounds = 0;
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
   while (n_active > 0 && rounds < max_rounds) {
-    launch_ctrl_begin(S, st), h->launches++;
+    ODE_LAUNCH(PC_CTRL, launch_ctrl_begin(S, st));
     if (h->any_1loop)
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, h->any_pr, with_jlo, st);
-    launch_output(S, h->d_kgrid, st), h->launches++;
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, h->any_pr, with_jlo, st, h->prof);
+    ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
     for (int s = 1; s < RK_STAGES; s++) {
-      launch_combine(S, s, S.flag_step, st), h->launches++;
+      ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.flag_step, st));
       if (h->any_full)
-        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, h->any_pr, 0, st);
-      launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st), h->launches++;
+        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, h->any_pr, 0, st, h->prof);
+      ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st));
     }
-    launch_final(S, S.flag_step, st), h->launches++;
-    launch_ctrl_end(S, h->cfg.max_attempts, st), h->launches++;
-    launch_accept(S, st), h->launches++;
+    ODE_LAUNCH(PC_FINAL, launch_final(S, S.flag_step, st));
+    ODE_LAUNCH(PC_CTRL, launch_ctrl_end(S, h->cfg.max_attempts, st));
+    ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
     if (h->any_full)
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, h->any_pr, 0, st);
-    launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st), h->launches++;
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, h->any_pr, 0, st, h->prof);
+    ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st));
     CU(cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     rounds++;
@@ -625,8 +668,12 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   std::vector<Cosmo> cs(B);
   CU(cudaMemcpyAsync(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  prof_collect(h);
   int worst = RTRG_OK;
   for (int b = 0; b < B; b++) {
+    // + the evaluation at z1l (1-loop cache, rtrg_device_init) or of the first dydt_in (full)
+    if (h->cos[b].c.sw_nl) h->counters[4 * b + 3] += 1;
+    h->counters[4 * b + 2] += 1;  // the first dydt_in
     if (status) status[b] = cs[b].status;
     if (cs[b].status) worst = RTRG_EODE;
   }
@@ -641,6 +688,27 @@ int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
   return RTRG_OK;
 }
 long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
+
+int rtrg_set_profiling(rtrg_handle *h, int on) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  h->prof = on ? &h->profiler : nullptr;
+  for (int i = 0; i < PC_NCAT; i++) h->prof_ms[i] = 0, h->prof_n[i] = 0;
+  h->profiler.reset();
+  return RTRG_OK;
+}
+int rtrg_profile_categories(void) { return PC_NCAT; }
+const char *rtrg_profile_name(int cat) {
+  static const char *names[PC_NCAT] = {"k_extrap", "k_bilinear", "k_jlo", "k_pz", "k_assemble", "k_rhs",
+                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_beta_reduce",
+                                       "k_growth_ode", "k_growth_tabs", "k_qag", "k_init_state"};
+  return (cat >= 0 && cat < PC_NCAT) ? names[cat] : "";
+}
+int rtrg_profile_query(const rtrg_handle *h, int cat, long long *n_launches, double *total_ms) {
+  if (!h || cat < 0 || cat >= PC_NCAT) return RTRG_EINVAL;
+  if (n_launches) *n_launches = h->prof_n[cat];
+  if (total_ms) *total_ms = h->prof_ms[cat];
+  return RTRG_OK;
+}
 
 // ---------------------------------------------------------------------------- hooks
 static int hook_check(rtrg_handle *h, int icosmo) {
@@ -694,7 +762,7 @@ static int run_integrals_hook(rtrg_handle *h, int icosmo, const double *lnP3nk, 
   double *yslot = h->S.ytmp + (size_t)icosmo * N_U * nk;
   CU(cudaMemcpyAsync(yslot, lnP3nk, 3 * nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)N_U * nk, h->S.src, want_raw ? h->d_raw : nullptr,
-                                  h->d_hookmask, h->cos[icosmo].c.sw_pr, 1, h->stream);
+                                  h->d_hookmask, h->cos[icosmo].c.sw_pr, 1, h->stream, nullptr);
   return RTRG_OK;
 }
 
@@ -756,7 +824,7 @@ int rtrg_derivatives(rtrg_handle *h, int icosmo, double eta, const double *y, do
   CU(cudaMemcpyAsync(h->S.t + icosmo, &eta, sizeof(double), cudaMemcpyHostToDevice, st));
   const Cosmo &c = h->cos[icosmo].c;
   if (c.sw_nl && !c.sw_1l)
-    h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)n, h->S.src, nullptr, h->d_hookmask, c.sw_pr, 0, st);
+    h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)n, h->S.src, nullptr, h->d_hookmask, c.sw_pr, 0, st, nullptr);
   launch_rhs(h->S, h->d_kgrid, h->S.ytmp, h->S.ynew, -1, h->d_hookmask, st), h->launches++;
   CU(cudaMemcpyAsync(dy, h->S.ynew + (size_t)icosmo * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

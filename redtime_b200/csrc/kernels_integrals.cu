@@ -311,35 +311,45 @@ size_t bilinear_smem_bytes(const IntegralTabs &tb) {
 // Returns the number of kernel launches.
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
-                     cudaStream_t st) {
+                     cudaStream_t st, Profiler *prof) {
   const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
   int launches = 0;
   {
     dim3 g((tb.np + 127) / 128, B);
+    RT_TIC(prof, PC_EXTRAP, st);
     k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask);
+    RT_TOC(prof, st);
     launches++;
   }
   {
     const int nkern = with_jn0 ? N_JKERN : 7;
     dim3 g((nrows / BIL_R) * tb.nchunk, nkern, B);
+    RT_TIC(prof, PC_BILINEAR, st);
     k_bilinear<BIL_R, BIL_TPB>
         <<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+    RT_TOC(prof, st);
     launches++;
   }
   if (with_jlo) {
+    RT_TIC(prof, PC_JLO, st);
     k_jlo<<<B, 256, tb.nsup * sizeof(double), st>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
+    RT_TOC(prof, st);
     launches++;
   }
   {
     dim3 g(N_ZKERN * 3, B);
     const double pre = tb.dlnk / (2.0 * M_PI * M_PI);  // rt:719
+    RT_TIC(prof, PC_PZ, st);
     k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask);
+    RT_TOC(prof, st);
     launches++;
   }
   {
     dim3 g((nrows + ASM_ROWS - 1) / ASM_ROWS, B);
+    RT_TIC(prof, PC_ASSEMBLE, st);
     k_assemble<<<g, 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
                                   nrows, mask);
+    RT_TOC(prof, st);
     launches++;
   }
   return launches;

@@ -262,16 +262,26 @@ __global__ void k_hook_plin(Batch S, int b, int which, double z, const double *k
 }
 
 // ---- launch sequence of the device-side initialisation ----------------------------------
-int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st) {
+int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof) {
   int n = 0;
   const int B = S.B;
+  RT_TIC(prof, PC_BETA_REDUCE, st);
   k_beta_reduce<<<dim3((S.nkk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  RT_TOC(prof, st);
+  RT_TIC(prof, PC_GROWTH_ODE, st);
   k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;
+  RT_TOC(prof, st);
+  RT_TIC(prof, PC_GROWTH_TABS, st);
   k_growth_norm<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;
   k_growth_rows<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
   k_tgrid<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  RT_TOC(prof, st);
+  RT_TIC(prof, PC_QAG, st);
   k_qag<<<B, 32, 0, st>>>(S), n++;
+  RT_TOC(prof, st);
+  RT_TIC(prof, PC_INIT_STATE, st);
   k_init_state<<<dim3((S.nk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
+  RT_TOC(prof, st);
   return n;
 }
 

@@ -167,10 +167,12 @@ __global__ void k_ctrl_begin(Batch S) {
     S.final_step[b] = fin;
     S.flag_step[b] = 1;
     S.m_full_step[b] = (c.sw_nl && !c.sw_1l);
+    if (S.m_full_step[b]) S.counters[4LL * b + 3] += 5;  // integral evaluations of stages 2..6
     S.rmax_bits[b] = (unsigned long long)__double_as_longlong(DBL_MIN);
   } else {
     S.flag_out[b] = 1;
     S.m_out_int[b] = (c.sw_nl && c.sw_1l);  // rt:1646
+    if (S.m_out_int[b]) S.counters[4LL * b + 3] += 1;
   }
 }
 
@@ -215,6 +217,7 @@ __global__ void k_ctrl_end(Batch S, int max_attempts) {
   S.h[b] = h0;
   S.flag_acc[b] = 1;
   S.m_full_acc[b] = (c.sw_nl && !c.sw_1l);
+  if (S.m_full_acc[b]) cnt[3] += 1;
   cnt[2] += 1;
   if (cnt[0] >= max_attempts) {
     c.status = RTRG_ODE_FAIL;

@@ -16,6 +16,10 @@
 //   weight tables      Tc     [14][NUp][ldT]         compact circulant kernels (L2 resident)
 #pragma once
 #include "rtrg_math.h"
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#include <vector>
+#endif
 
 namespace rtrg {
 
@@ -93,6 +97,40 @@ struct Batch {
   double *hdr;             // [B][MAX_OUT][5]
   double *hdr0;            // [B][2]
 };
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
+// numbers).  Off by default: a null Profiler* costs nothing.
+enum ProfCat {
+  PC_EXTRAP, PC_BILINEAR, PC_JLO, PC_PZ, PC_ASSEMBLE, PC_RHS, PC_COMBINE, PC_FINAL, PC_CTRL,
+  PC_ACCEPT, PC_OUTPUT, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
+  PC_NCAT
+};
+#ifdef __CUDACC__
+struct Profiler {
+  struct Rec { int cat; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void tic(int cat, cudaStream_t st) {
+    Rec r = {cat, get(), get()};
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void toc(cudaStream_t st) { cudaEventRecord(recs.back().e1, st); }
+  void reset() { recs.clear(); used = 0; }
+  ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+#define RT_TIC(prof, cat, st) do { if (prof) (prof)->tic(cat, st); } while (0)
+#define RT_TOC(prof, st) do { if (prof) (prof)->toc(st); } while (0)
+#endif
 
 RT_HD BetaTab beta_tab(const Batch &S, const Cosmo &c) {
   BetaTab t;

@@ -250,31 +250,57 @@ RT_HD double beta_row(const BetaTab &t, const double *brow, double a, long long 
 // explicit embedded Runge-Kutta tableaux (GSL rkf45.c / rk8pd.c)
 // ------------------------------------------------------------------------------------
 struct RKF45 {
-  // nodes, rows, 5th-order weights (propagated), error weights
+  // nodes, rows, 5th-order weights (propagated), error weights.  Written as switches so that
+  // device code holds no local constant arrays.
   static RT_HD double c(int s) {
-    const double v[6] = {0.0, 1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
-    return v[s];
+    switch (s) {
+      case 1: return 1.0 / 4.0;
+      case 2: return 3.0 / 8.0;
+      case 3: return 12.0 / 13.0;
+      case 4: return 1.0;
+      case 5: return 1.0 / 2.0;
+      default: return 0.0;
+    }
   }
   static RT_HD double a(int s, int j) {
-    const double v[6][5] = {
-        {0, 0, 0, 0, 0},
-        {1.0 / 4.0, 0, 0, 0, 0},
-        {3.0 / 32.0, 9.0 / 32.0, 0, 0, 0},
-        {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0, 0, 0},
-        {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0, 0},
-        {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0,
-         -5643.0 / 20520.0}};
-    return v[s][j];
+    switch (8 * s + j) {
+      case 8 * 1 + 0: return 1.0 / 4.0;
+      case 8 * 2 + 0: return 3.0 / 32.0;
+      case 8 * 2 + 1: return 9.0 / 32.0;
+      case 8 * 3 + 0: return 1932.0 / 2197.0;
+      case 8 * 3 + 1: return -7200.0 / 2197.0;
+      case 8 * 3 + 2: return 7296.0 / 2197.0;
+      case 8 * 4 + 0: return 8341.0 / 4104.0;
+      case 8 * 4 + 1: return -32832.0 / 4104.0;
+      case 8 * 4 + 2: return 29440.0 / 4104.0;
+      case 8 * 4 + 3: return -845.0 / 4104.0;
+      case 8 * 5 + 0: return -6080.0 / 20520.0;
+      case 8 * 5 + 1: return 41040.0 / 20520.0;
+      case 8 * 5 + 2: return -28352.0 / 20520.0;
+      case 8 * 5 + 3: return 9295.0 / 20520.0;
+      case 8 * 5 + 4: return -5643.0 / 20520.0;
+      default: return 0.0;
+    }
   }
   static RT_HD double b(int j) {
-    const double v[6] = {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0,
-                         3855735.0 / 7618050.0, -1371249.0 / 7618050.0, 277020.0 / 7618050.0};
-    return v[j];
+    switch (j) {
+      case 0: return 902880.0 / 7618050.0;
+      case 2: return 3953664.0 / 7618050.0;
+      case 3: return 3855735.0 / 7618050.0;
+      case 4: return -1371249.0 / 7618050.0;
+      case 5: return 277020.0 / 7618050.0;
+      default: return 0.0;
+    }
   }
   static RT_HD double e(int j) {
-    const double v[6] = {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0,
-                         2.0 / 55.0};
-    return v[j];
+    switch (j) {
+      case 0: return 1.0 / 360.0;
+      case 2: return -128.0 / 4275.0;
+      case 3: return -2197.0 / 75240.0;
+      case 4: return 1.0 / 50.0;
+      case 5: return 2.0 / 55.0;
+      default: return 0.0;
+    }
   }
 };
 
@@ -739,32 +765,31 @@ RT_HD int i64_slot(int J) {
   }
 }
 RT_HD int nAI(int a, int c, int d, int b, int e, int f) { return 32 * a + 16 * c + 8 * d + 4 * b + 2 * e + f; }
-// the unique components (rt:151-157)
+// the unique components (rt:151-157): a = c = (j >= 8), d = 1, and (b,e,f) the binary digits of
+// j for j < 8, of {0,1,3,4,5,7}[j-8] otherwise.  Pure arithmetic: no local tables in device code.
 RT_HD void unique_abcdef(int j, int *a, int *c, int *d, int *b, int *e, int *f) {
-  const int aU[14] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
-  const int bU[14] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1};
-  const int eU[14] = {0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 1};
-  const int fU[14] = {0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 0, 1, 1};
-  *a = aU[j]; *c = aU[j]; *d = 1; *b = bU[j]; *e = eU[j]; *f = fU[j];
+  const int hi = (j >= 8);
+  const int bef = hi ? ((0x754310 >> (4 * (j - 8))) & 7) : j;
+  *a = hi; *c = hi; *d = 1; *b = (bef >> 2) & 1; *e = (bef >> 1) & 1; *f = bef & 1;
 }
 
 // y[41] -> dy[41] for one k.  A14: the 14 unique A_{acd,bef}; R24: R^ell_{abc}.
 // Om10 = Omega(1,0), Om11 = Omega(1,1) (rt:1395-1401).  evolve_Q: rt:1516.
 RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonlinear, int evolve_Q,
                        const double *y, const double *A14, const double *R24, double *dy) {
-  const double Om[2][2] = {{1.0, -1.0}, {Om10, Om11}};
+  // Omega(i,j) (rt:1383-1411) without a local table
+#define RT_OM(i, j) ((i) == 0 ? ((j) == 0 ? 1.0 : -1.0) : ((j) == 0 ? Om10 : Om11))
   const double eeta = exp(eta);
   const double P[3] = {exp(y[0]), exp(y[1]), exp(y[2])};
   double dP[3] = {0, 0, 0};
   for (int c = 0; c < 2; c++) {
-    dP[0] -= Om[0][c] * P[c] + Om[0][c] * P[c];
-    dP[1] -= Om[0][c] * P[c + 1] + Om[1][c] * P[c];
-    dP[2] -= Om[1][c] * P[c + 1] + Om[1][c] * P[c + 1];
+    dP[0] -= RT_OM(0, c) * P[c] + RT_OM(0, c) * P[c];
+    dP[1] -= RT_OM(0, c) * P[c + 1] + RT_OM(1, c) * P[c];
+    dP[2] -= RT_OM(1, c) * P[c + 1] + RT_OM(1, c) * P[c + 1];
     if (nonlinear) {
       for (int d = 0; d < 2; d++) {
-        const int ab[3][2] = {{0, 0}, {1, 0}, {1, 1}};
         for (int q = 0; q < 3; q++) {
-          const int a = ab[q][0], b = ab[q][1];
+          const int a = (q > 0), b = (q > 1);  // (a,b) = 00, 10, 11
           const int s0 = i64_slot(nAI(a, c, d, b, c, d)), s1 = i64_slot(nAI(b, c, d, a, c, d));
           const double I0 = s0 >= 0 ? y[N_UP + s0] : 0.0, I1 = s1 >= 0 ? y[N_UP + s1] : 0.0;
           dP[q] += eeta * 4.0 * M_PI / k * (I0 + I1);
@@ -788,7 +813,7 @@ RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonli
                 s3 = i64_slot(nAI(a, c, d, b, e, g));
       const double I1 = s1 >= 0 ? y[N_UP + s1] : 0.0, I2 = s2 >= 0 ? y[N_UP + s2] : 0.0,
                    I3 = s3 >= 0 ? y[N_UP + s3] : 0.0;
-      v += -Om[b][g] * I1 - Om[e][g] * I2 - Om[f][g] * I3;
+      v += -RT_OM(b, g) * I1 - RT_OM(e, g) * I2 - RT_OM(f, g) * I3;
     }
     dy[N_UP + j] = v;
   }
@@ -801,13 +826,15 @@ RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonli
             const int j = 4 * a + 2 * b + c;
             double v = 2.0 * eeta * R24[8 * l + j];
             for (int d = 0; d < 2; d++)
-              v += -Om[a][d] * Q[4 * d + 2 * b + c] - Om[b][d] * Q[4 * a + 2 * d + c] -
-                   Om[c][d] * Q[4 * a + 2 * b + d];
+              v += -RT_OM(a, d) * Q[4 * d + 2 * b + c] - RT_OM(b, d) * Q[4 * a + 2 * d + c] -
+                   RT_OM(c, d) * Q[4 * a + 2 * b + d];
             dy[N_UP + N_UI + 8 * l + j] = v;
           }
     }
   }
 }
+
+#undef RT_OM
 
 // Omega(1,0) and Omega(1,1) (rt:1395-1401)
 RT_HD void trg_omega(const Cosmo &c, double A, double beta, double *Om10, double *Om11) {

@@ -101,8 +101,11 @@ def main():
                 return conftest.parse_tables(f.read())[1]
         gold = load("example1/example_redTime_result.dat.gz")
         o1, o2 = load("example1_oracle_1loop.dat.gz"), load("example1_oracle_full.dat.gz")
-        e2e("1loop", d1, [("reference golden (genuine GSL)", gold), ("oracle", o1)])
-        e2e("full TRG", d2, [("oracle", o2)])
+        t1 = e2e("1loop", d1, [("reference golden (genuine GSL)", gold), ("oracle", o1)])
+        t2 = e2e("full TRG", d2, [("oracle", o2)])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", "e2e_tables.npz"), t1=t1, t2=t2)
+        print("DFMA peak TFLOP/s:", rt.dfma_peak_tflops(0, 0.5))
 
 
 if __name__ == "__main__":
