@@ -123,6 +123,10 @@ int rtrg_profile_categories(void);
 const char *rtrg_profile_name(int cat);
 int rtrg_profile_query(const rtrg_handle *h, int cat, long long *n_launches, double *total_ms);
 
+/* Tuning aid: evaluate the mode-coupling integrals of the linear spectra at z1l for every
+ * cosmology of the batch `reps` times (all 14 bilinear kernels); read the timings with
+ * rtrg_profile_query().  Results go to the scratch source buffer only.                  */
+int rtrg_bench_integrals(rtrg_handle *h, int reps);
 /* FP64 FMA pipe peak of `device` in TFLOP/s (register-resident DFMA loop, best launch over
  * about `seconds` of device time): the roofline denominator of the integral kernels.    */
 int rtrg_bench_dfma(int device, double seconds, double *tflops);

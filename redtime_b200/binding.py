@@ -70,6 +70,7 @@ def load_library():
     lib.rtrg_profile_name.restype = C.c_char_p
     lib.rtrg_profile_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _dp]
     lib.rtrg_bench_dfma.argtypes = [C.c_int, C.c_double, _dp]
+    lib.rtrg_bench_integrals.argtypes = [C.c_void_p, C.c_int]
     lib.rtrg_run.argtypes = [C.c_void_p, _dp, C.c_size_t, _dp, _dp, _ip]
     lib.rtrg_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     lib.rtrg_extrap_P.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -271,6 +272,9 @@ class RedTimeB200:
         status = np.zeros(self.n_cosmo, np.int32)
         _check(self.lib.rtrg_run(self.h, None, 0, None, None, status.ctypes.data_as(_ip)))
         return status
+
+    def bench_integrals(self, reps=1):
+        _check(self.lib.rtrg_bench_integrals(self.h, int(reps)))
 
     def set_profiling(self, on=True):
         _check(self.lib.rtrg_set_profiling(self.h, int(on)))

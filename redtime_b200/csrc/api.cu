@@ -689,6 +689,20 @@ int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
 }
 long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
 
+int rtrg_bench_integrals(rtrg_handle *h, int reps) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (!h->prepared) return fail(RTRG_EINVAL, "rtrg_prepare() has not been called");
+  CU(cudaSetDevice(h->cfg.device));
+  const int nk = h->S.nk;
+  for (int r = 0; r < reps; r++)
+    h->launches += launch_integrals(h->tb, h->S, h->S.y_z1l, 3LL * nk, h->S.src, nullptr, nullptr, 1,
+                                    h->cfg.print_bias, h->stream, h->prof);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  prof_collect(h);
+  return RTRG_OK;
+}
+
 int rtrg_set_profiling(rtrg_handle *h, int on) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   h->prof = on ? &h->profiler : nullptr;

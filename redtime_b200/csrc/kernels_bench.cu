@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 #pragma unroll 1
   for (int i = 0; i < iters; i++) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < 64; u++) {
       x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
       x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
     }
@@ -31,12 +31,12 @@ extern "C" int rtrg_bench_dfma(int device, double seconds, double *tflops) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   double *out = nullptr;
-  const int ctas = prop.multiProcessorCount * 8, tpb = 256, iters = 4096;
+  const int ctas = prop.multiProcessorCount * 8, tpb = 256, iters = 512;
   if (cudaMalloc(&out, (size_t)ctas * tpb * sizeof(double)) != cudaSuccess) return RTRG_ENOMEM;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const double flop = 2.0 * 64.0 * iters * (double)ctas * tpb;
+  const double flop = 2.0 * 512.0 * iters * (double)ctas * tpb;
   k_dfma_peak<<<ctas, tpb>>>(out, iters, 0.999999, 1e-9);  // warm-up
   cudaDeviceSynchronize();
   double best = 0, spent = 0;

@@ -17,6 +17,7 @@
 // shared memory as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles.
 // Algorithmic work per (cosmology, n): 2*9*nk*nsup^2 FLOP; executed: 2*3*nk*(nsup+7)^2.
 #include <cstdint>
+#include <cstdlib>
 
 #include "rtrg_device.h"
 
@@ -94,8 +95,35 @@ __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
 }
 
 // ---------------------------------------------------------------------------- k_bilinear
-template <int R, int TPB>
-__global__ void __launch_bounds__(TPB)
+// Sum V values per lane over the 32 lanes of a warp by recursive halving: after the call the
+// lanes with (lane & 3) == 0 hold, in v[0..V/8), the totals of the value indices
+//   ((lane>>4)&1) * V/2 + ((lane>>3)&1) * V/4 + ((lane>>2)&1) * V/8 + i.
+// V + V/4 double shuffles instead of 5 V for V independent butterfly reductions.
+template <int V>
+__device__ __forceinline__ void warp_sum_multi(double (&v)[V], int lane) {
+  static_assert(V % 8 == 0, "V must be a multiple of 8");
+#pragma unroll
+  for (int lvl = 0; lvl < 3; lvl++) {
+    const int half = V >> (lvl + 1), bit = 16 >> lvl;
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V / 8; i++) {
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+  }
+}
+
+// R: output rows per CTA; TPB: threads (one alpha-side lag each); MINB: CTAs per SM the
+// register budget is tuned for; VC: beta-side lags per software-pipelined chunk.
+template <int R, int TPB, int MINB, int VC>
+__global__ void __launch_bounds__(TPB, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
                double *__restrict__ Jpart, int n_first, int row0, const int *__restrict__ mask) {
   const int e = blockIdx.z;
@@ -127,50 +155,55 @@ __global__ void __launch_bounds__(TPB)
   double acc[R][3];
 #pragma unroll
   for (int r = 0; r < R; r++) acc[r][0] = acc[r][1] = acc[r][2] = 0.0;
-  double tcur[R], tnxt[R];
+  double tcur[VC], tnxt[VC];
 #pragma unroll
-  for (int s = 0; s < R; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
+  for (int s = 0; s < VC; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
 
   mbar_wait(&mbar, 0);
 
   const int NVp = tb.NVp;
-  for (int tv0 = 0; tv0 < NVp; tv0 += R) {
-    if (tv0 + R < NVp) {
-      const double *Tn = Tp + (size_t)(tv0 + R) * ldT;
+  constexpr int NW = (VC + R) / 2;  // double2 loads covering the VC + R - 1 window values
+  for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
+    if (tv0 + VC < NVp) {
+      const double *Tn = Tp + (size_t)(tv0 + VC) * ldT;
 #pragma unroll
-      for (int s = 0; s < R; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
+      for (int s = 0; s < VC; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      // window w[q] = arev_c[tv0 + q - (R-1)], q in [0, 2R-1): 16-byte broadcast loads
-      double w[2 * R];
+      // window w[q] = arev_c[tv0 + q - (R-1)], q in [0, VC+R-1): 16-byte broadcast loads
+      double w[2 * NW];
       const double2 *wp = reinterpret_cast<const double2 *>(s_a + c * LP + tv0);
 #pragma unroll
-      for (int q = 0; q < R; q++) {
+      for (int q = 0; q < NW; q++) {
         const double2 v = wp[q];
         w[2 * q] = v.x;
         w[2 * q + 1] = v.y;
       }
 #pragma unroll
-      for (int s = 0; s < R; s++)
+      for (int s = 0; s < VC; s++)
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r][c] = fma(tcur[s], w[s - r + R - 1], acc[r][c]);
     }
 #pragma unroll
-    for (int s = 0; s < R; s++) tcur[s] = tnxt[s];
+    for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
   }
 
-  // alpha side: out[r][ab][cd] = sum_u arev_ab[u - r] * S_u[r][cd]
+  // alpha side: out[ab][cd][r] = sum_u arev_ab[u - r] * S_u[r][cd].  Eight rows at a time go
+  // through the halving reduction; lane 4*r then holds row r.
+  static_assert(R == 8, "the epilogue reduction is written for 8 rows per CTA");
 #pragma unroll
-  for (int r = 0; r < R; r++) {
+  for (int ab = 0; ab < 3; ab++) {
+    double m[R];
 #pragma unroll
-    for (int ab = 0; ab < 3; ab++) {
-      const double m = active ? s_a[ab * LP + (R - 1) + tu - r] : 0.0;
+    for (int r = 0; r < R; r++) m[r] = active ? s_a[ab * LP + (R - 1) + tu - r] : 0.0;
 #pragma unroll
-      for (int cd = 0; cd < 3; cd++) {
-        const double x = warp_sum(m * acc[r][cd]);
-        if (lane == 0) s_red[warp * (9 * R) + (ab * 3 + cd) * R + r] = x;
-      }
+    for (int cd = 0; cd < 3; cd++) {
+      double prod[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) prod[r] = m[r] * acc[r][cd];
+      warp_sum_multi<R>(prod, lane);
+      if ((lane & 3) == 0) s_red[warp * (9 * R) + (ab * 3 + cd) * R + (lane >> 2)] = prod[0];
     }
   }
   __syncthreads();
@@ -302,6 +335,9 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------- launchers
 enum { BIL_TPB = 352 };
+// kernel variant (tuning knob, RTRG_BIL_VARIANT): 0 = 2 CTAs/SM, 8-lag chunks (default);
+// 1 = 1 CTA/SM, 8-lag chunks; 2 = 2 CTAs/SM, 4-lag chunks
+static int g_bil_variant = 0;
 
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
   return (size_t)(3 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
@@ -325,8 +361,17 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     const int nkern = with_jn0 ? N_JKERN : 7;
     dim3 g((nrows / BIL_R) * tb.nchunk, nkern, B);
     RT_TIC(prof, PC_BILINEAR, st);
-    k_bilinear<BIL_R, BIL_TPB>
-        <<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+    const size_t smem = bilinear_smem_bytes(tb);
+    switch (g_bil_variant) {
+      case 1:
+        k_bilinear<BIL_R, BIL_TPB, 1, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+        break;
+      case 2:
+        k_bilinear<BIL_R, BIL_TPB, 2, 4><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+        break;
+      default:
+        k_bilinear<BIL_R, BIL_TPB, 2, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
+    }
     RT_TOC(prof, st);
     launches++;
   }
@@ -362,8 +407,12 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 }
 
 int integrals_configure() {
+  const char *v = getenv("RTRG_BIL_VARIANT");
+  g_bil_variant = (v && *v) ? atoi(v) : 0;
   // opt in to the dynamic shared memory the bilinear kernel may need for large grids
-  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB>,
+  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
 

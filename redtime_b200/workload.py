@@ -31,7 +31,7 @@ def extract_example1(dst):
     os.makedirs(dst, exist_ok=True)
     with lzma.open(os.path.join(EXAMPLE1, "camb_transfers.tar.xz")) as f:
         with tarfile.open(fileobj=f) as tar:
-            tar.extractall(dst)
+            tar.extractall(dst, filter="data")
     with open(os.path.join(EXAMPLE1, "params_redTime.dat")) as f:
         txt = f.read()
     with open(os.path.join(dst, "params_redTime.dat"), "w") as f:

@@ -23,7 +23,7 @@ def make_example1_dir(dst, switches=None, z_out=None):
     os.makedirs(dst, exist_ok=True)
     with lzma.open(os.path.join(GOLDEN, "example1", "camb_transfers.tar.xz")) as f:
         with tarfile.open(fileobj=f) as tar:
-            tar.extractall(dst)
+            tar.extractall(dst, filter="data")
     src = open(os.path.join(GOLDEN, "example1", "params_redTime.dat")).read().split("\n")
     if switches is not None or z_out is not None:
         vals = [i for i, l in enumerate(src) if l.strip() and not l.startswith("#")]

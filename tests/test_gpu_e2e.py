@@ -47,15 +47,22 @@ def test_example1_1loop(example1_dir, golden_example1):
     assert tab.shape == (7, NK, 17)
     # the step sequence genuine GSL took
     assert (cnt["attempts"], cnt["rejected"]) == (23, 4)
+    k = gold[0, :, 0]
     for ref in (gold, orc):
         e = col_err(tab, ref)
-        assert np.all(e[:7] < 1e-6), e
-        assert np.all(e[7:10] < 1e-5), e
-        hi = ref[0, :, 0] > 5.7e-3
-        assert np.all(col_err(tab[:, hi], ref[:, hi])[10:] < 1e-5), e
-    # low-k rows of columns 11-17: not noisier than genuine GSL vs the oracle
-    floor = np.abs(gold - orc)
-    assert np.all(np.abs(tab - orc)[:, :, 10:] <= 1e-5 * np.abs(orc[:, :, 10:]) + 4 * floor[:, :, 10:] + 1e-300)
+        assert np.all(e[:7] < 1e-6), e      # columns 1-7
+        assert np.all(e[7:15] < 1e-5), e    # columns 8-15 at every k
+        hi = k > 3.3e-3
+        assert np.all(col_err(tab[:, hi], ref[:, hi])[15:] < 1e-5), e
+    # Columns 16-17 (P_T,6, P_T,8) below k = 3.3e-3 h/Mpc are 1e3..1e9-fold cancellations of the
+    # J integrals: there the reference linked to genuine GSL and the same sources linked to a
+    # different FFT (the oracle) already disagree by up to 8e-2.  Bound our
+    # distance to the oracle by that measured floor: 1e-5 + 5 x (floor of the row and its
+    # neighbours, max over redshifts).
+    rel_go = np.max(np.abs(gold - orc) / (np.abs(orc) + 1e-300), axis=0)  # [k, col]
+    rel_to = np.max(np.abs(tab - orc) / (np.abs(orc) + 1e-300), axis=0)
+    floor = np.maximum(rel_go, np.maximum(np.roll(rel_go, 1, axis=0), np.roll(rel_go, -1, axis=0)))
+    assert np.all(rel_to[:, 15:] <= 1e-5 + 5 * floor[:, 15:]), rel_to[:24, 15:]
 
 
 def test_example1_header_lines(example1_dir, golden_example1, tmp_path):
@@ -75,8 +82,7 @@ def test_example1_full_trg(example1_full_dir):
     e = col_err(tab, orc)
     assert np.all(e[:7] < 1e-6), e
     assert np.all(e[7:10] < 1e-5), e
-    hi = orc[0, :, 0] > 5.7e-3
-    assert np.all(col_err(tab[:, hi, :13], orc[:, hi, :13])[10:] < 1e-5), e
+    assert np.all(e[10:13] < 1e-5), e
     assert not tab[:, :, 13:].any()  # columns 14-17 are zeros in full-TRG mode
 
 

@@ -1,0 +1,78 @@
+"""Host side of the drop-in boundary: params_redTime.dat / CAMB readers and the table printer
+(reference: src/AU_cosmological_parameters.h:231-353,547-627,790-832; src/redTime.cc:1602-1741)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import redtime_b200 as rt
+from redtime_b200 import workload as wl
+from conftest import GOLDEN, make_example1_dir
+
+
+def test_read_example1(example1_dir):
+    d = rt.read_run_dir(example1_dir)
+    assert np.allclose(d["params"], [0.87969, 0.80560, 0.73418, 0.286233679143621, 0.0430930827493416, 0.00576437405571056,
+                                     2.726, -1.2147, -1.112],
+                       rtol=0, atol=1e-15)
+    assert d["switches"] == [1, 1, 1, 1] and d["z_in"] == 200
+    assert list(d["z_out"]) == [5, 4, 3, 2, 1, 0.5, 0]
+    assert list(d["z_interp"]) == [200, 100, 50, 20, 10, 5, 4, 3, 2, 1, 0.5, 0]
+    assert d["k_T"].size == 15447 and d["Tc_b"].shape == (12, 15447) and d["Tnu_b"].shape == (12, 15447)
+    assert np.all(np.diff(d["k_T"]) > 0) and np.array_equal(d["k_T"], d["k_b"])
+    assert np.array_equal(d["Tc_T"], d["Tc_b"][-1])  # the z=0 file is also the last interpolation file
+
+
+def test_missing_inputs_are_errors(tmp_path):
+    with pytest.raises(rt.RtrgError):
+        rt.read_run_dir(str(tmp_path))
+    d = make_example1_dir(str(tmp_path / "x"))
+    os.remove(os.path.join(d, "camb_transfer_z3.dat"))
+    with pytest.raises(rt.RtrgError):
+        rt.read_run_dir(d)
+
+
+def test_massless_neutrinos_need_only_the_z0_file(tmp_path):
+    """hdr:523-525: with f_nu < 1e-10 the interpolation files are never opened."""
+    d = make_example1_dir(str(tmp_path / "x"))
+    lines = open(os.path.join(d, "params_redTime.dat")).read().split("\n")
+    vals = [i for i, l in enumerate(lines) if l.strip() and not l.startswith("#")]
+    lines[vals[5]] = "0.0"
+    open(os.path.join(d, "params_redTime.dat"), "w").write("\n".join(lines))
+    for z in ("200", "100", "50"):
+        os.remove(os.path.join(d, "camb_transfer_z%s.dat" % z))
+    c = rt.read_run_dir(d)
+    assert c["z_interp"].size == 0 and c["k_b"].size == 0 and c["k_T"].size == 15447
+
+
+def test_written_run_dir_round_trips(tmp_path):
+    base = wl.load_example1(subsample=64)
+    c = wl.make_cosmologies(3, base)[2]
+    d = rt.read_run_dir(wl.write_run_dir(str(tmp_path / "c"), c))
+    for key in ("params", "z_out", "k_T", "Tc_T", "Tb_T", "Tc_b", "Tnu_b", "z_interp"):
+        assert np.array_equal(np.asarray(d[key]), np.asarray(c[key])), key
+
+
+def test_printer_reproduces_the_reference_stdout(tmp_path, golden_example1):
+    """Feeding the golden's own numbers through rtrg_print_result must give back the golden
+    file: banner, '###main' lines, setw(20)/setprecision(12) rows, two blank lines per block."""
+    hdr_lines, arr = golden_example1
+    with gzip.open(os.path.join(GOLDEN, "example1", "example_redTime_result.dat.gz"), "rt") as f:
+        ref_text = f.read()
+    tab = arr.reshape(7, 128, 17)
+    import re
+    hdr0 = np.array([float(x) for x in re.findall(r"= ([0-9.eE+-]+)", hdr_lines[1])])
+    hdr = np.zeros((7, 5))
+    for i, l in enumerate(hdr_lines[2:]):
+        hdr[i] = [float(x) for x in re.findall(r"=([0-9.eE+-]+)", l)]
+    p = str(tmp_path / "o.dat")
+    rt.print_result(p, 128, tab, hdr, hdr0)
+    mine = open(p).read()
+    assert mine.split("\n")[:3] == ref_text.split("\n")[:3]
+    # 12 significant digits survive the parse -> print round trip for all but last-digit ties
+    ml, rl = mine.split("\n"), ref_text.split("\n")
+    assert len(ml) == len(rl)
+    same = sum(a == b for a, b in zip(ml, rl))
+    assert same >= 0.99 * len(rl)
+    assert all(len(a) == len(b) for a, b in zip(ml, rl))
