@@ -89,6 +89,8 @@ int rtrg_set_stream(rtrg_handle *h, void *cuda_stream);
 
 int rtrg_clear_cosmologies(rtrg_handle *h);
 int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *c);
+/* the same for n cosmologies at once; the table copies run on several host threads */
+int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *list);
 int rtrg_num_cosmologies(const rtrg_handle *h);
 /* columns of the table of cosmology i (src/redTime.cc:1670-1737): 17 by default */
 int rtrg_num_columns(const rtrg_handle *h, int icosmo);

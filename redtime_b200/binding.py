@@ -61,6 +61,7 @@ def load_library():
     lib.rtrg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtrg_clear_cosmologies.argtypes = [C.c_void_p]
     lib.rtrg_add_cosmology.argtypes = [C.c_void_p, C.POINTER(_Cosmology)]
+    lib.rtrg_add_cosmologies.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(_Cosmology))]
     lib.rtrg_num_cosmologies.argtypes = [C.c_void_p]
     lib.rtrg_num_columns.argtypes = [C.c_void_p, C.c_int]
     lib.rtrg_prepare.argtypes = [C.c_void_p]
@@ -233,7 +234,8 @@ class RedTimeB200:
         _check(self.lib.rtrg_clear_cosmologies(self.h))
         self._keep, self._nout = [], []
 
-    def add_cosmology(self, d):
+    @staticmethod
+    def _struct(d):
         c = _Cosmology()
         for i in range(9):
             c.params[i] = float(d["params"][i])
@@ -249,9 +251,22 @@ class RedTimeB200:
         c.z_interp = _P(keep["z_interp"])
         c.n_kb = keep["k_b"].size
         c.k_b, c.Tc_b, c.Tnu_b = _P(keep["k_b"]), _P(keep["Tc_b"]), _P(keep["Tnu_b"])
+        return c, keep
+
+    def add_cosmology(self, d):
+        """d: dict with params[9], switches[4], z_in, z_out, k_T, Tc_T, Tb_T, z_interp, k_b,
+        Tc_b[n_z][n_kb], Tnu_b[n_z][n_kb] (the library copies the arrays)."""
+        c, keep = self._struct(d)
         _check(self.lib.rtrg_add_cosmology(self.h, C.byref(c)))
         self._nout.append(int(c.n_out))
         return len(self._nout) - 1
+
+    def add_cosmologies(self, dicts):
+        """Batch form of add_cosmology: one C-ABI call, table copies on several host threads."""
+        structs = [self._struct(d) for d in dicts]
+        arr = (C.POINTER(_Cosmology) * len(structs))(*[C.pointer(c) for c, _ in structs])
+        _check(self.lib.rtrg_add_cosmologies(self.h, len(structs), arr))
+        self._nout.extend(int(c.n_out) for c, _ in structs)
 
     @property
     def n_cosmo(self):

@@ -27,6 +27,7 @@ int integrals_configure();
 // kernels_linear.cu
 int linear_upload_constants();
 int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof);
+int launch_prep_inputs(const Batch &S, double *T0, int max_rows, cudaStream_t st, Profiler *prof);
 void launch_hook_DdD(const Batch &S, int b, double z, const double *k, int n, double *D, double *dD,
                      int *err, cudaStream_t st);
 void launch_hook_beta(const Batch &S, int b, double a, const double *k, int n, double *beta, int *err,
@@ -65,8 +66,49 @@ static int fail(int code, const char *fmt, ...) {
   } while (0)
 
 struct HostCosmo {
-  Cosmo c;
-  std::vector<double> z_out, lnkT, lnT, anodes, kb, beta;
+  Cosmo c;  // offsets point into the staging arena (= the device input pool)
+  std::vector<double> z_out;
+};
+
+// Pinned host arena mirroring the device input pool: rtrg_add_cosmology copies the caller's
+// buffers here (the caller owns its buffers and may free them right away); rtrg_prepare sends
+// the not-yet-uploaded tail to the device with one asynchronous copy.
+struct StagingArena {
+  double *base = nullptr;
+  size_t cap = 0, used = 0;
+  int reserve(size_t n_total) {
+    if (n_total <= cap) return RTRG_OK;
+    size_t ncap = std::max(n_total, cap + cap / 2);
+    double *nb = nullptr;
+    if (cudaHostAlloc((void **)&nb, ncap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return RTRG_ENOMEM;
+    }
+    if (used) std::memcpy(nb, base, used * sizeof(double));
+    if (base) cudaFreeHost(base);
+    base = nb;
+    cap = ncap;
+    return RTRG_OK;
+  }
+  void release() {
+    if (base) cudaFreeHost(base);
+    base = nullptr;
+    cap = used = 0;
+  }
+};
+
+// One device allocation carved into the batch work buffers; kept across rtrg_prepare calls
+// while it is large enough (no cudaMalloc/cudaFree churn between batches).
+struct DeviceArena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  template <class T>
+  T *take(size_t n) {
+    used = (used + 255) & ~(size_t)255;
+    T *p = (T *)(base ? base + used : nullptr);
+    used += (n ? n : 1) * sizeof(T);
+    return p;
+  }
 };
 
 struct rtrg_handle {
@@ -75,6 +117,11 @@ struct rtrg_handle {
   cudaStream_t stream = nullptr, own_stream = nullptr;
   IntegralTabs tb;
   std::vector<void *> table_allocs, batch_allocs;
+  StagingArena stage;
+  DeviceArena work;
+  double *d_in = nullptr;     // device input pool (mirror of stage)
+  size_t d_in_cap = 0, d_in_uploaded = 0;
+  double *d_T0 = nullptr;
   double *d_kgrid = nullptr;
   std::vector<double> kgrid;
   std::vector<HostCosmo> cos;
@@ -355,6 +402,9 @@ int rtrg_destroy(rtrg_handle *h) {
   cudaSetDevice(h->cfg.device);
   free_pool(h->batch_allocs);
   free_pool(h->table_allocs);
+  if (h->work.base) cudaFree(h->work.base);
+  if (h->d_in) cudaFree(h->d_in);
+  h->stage.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RTRG_OK;
@@ -369,6 +419,8 @@ int rtrg_set_stream(rtrg_handle *h, void *cuda_stream) {
 int rtrg_clear_cosmologies(rtrg_handle *h) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   h->cos.clear();
+  h->stage.used = 0;
+  h->d_in_uploaded = 0;
   h->prepared = h->uploaded = false;
   return RTRG_OK;
 }
@@ -380,13 +432,21 @@ int rtrg_num_columns(const rtrg_handle *h, int i) {
   return num_columns(h->cfg, h->cos[i].c);
 }
 
-int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) {
-  if (!h || !in) return fail(RTRG_EINVAL, "null argument");
+static int check_cosmology(const rtrg_cosmology *in) {
+  if (!in) return fail(RTRG_EINVAL, "null cosmology");
   if (in->n_out < 1 || in->n_out > RTRG_MAX_OUT || !in->z_out) return fail(RTRG_EINVAL, "bad n_out");
   if (in->n_T < 4 || !in->k_T || !in->Tc_T || !in->Tb_T) return fail(RTRG_EINVAL, "bad transfer table");
   if (in->n_z < 0 || in->n_z > RTRG_MAX_Z || in->n_z == 1) return fail(RTRG_EINVAL, "bad n_z");
   if (in->n_z > 0 && (in->n_kb < 4 || !in->z_interp || !in->k_b || !in->Tc_b || !in->Tnu_b))
     return fail(RTRG_EINVAL, "bad interpolation tables");
+  return RTRG_OK;
+}
+static size_t cosmology_doubles(const rtrg_cosmology *in) {
+  const size_t nz = in->n_z > 0 ? in->n_z : 0, nkb = in->n_z > 0 ? in->n_kb : 0;
+  return 3 * (size_t)in->n_T + nz + nkb + 2 * nz * nkb;
+}
+// scalars + offsets of one cosmology whose tables start at arena offset `off`
+static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off) {
   HostCosmo hc;
   Cosmo &c = hc.c;
   std::memset(&c, 0, sizeof c);
@@ -397,39 +457,75 @@ int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) {
   c.sw_nl = in->switches[0], c.sw_1l = in->switches[1], c.sw_pl = in->switches[2], c.sw_pr = in->switches[3];
   c.n_out = in->n_out;
   hc.z_out.assign(in->z_out, in->z_out + in->n_out);
-  // z=0 transfer function: T_cb = f_b T_b + f_c T_c, tabulated as ln(T/T[0]) vs ln k (hdr:804-823)
-  const double f_b_cb = c.Ob / (c.Om - c.On), f_c_cb = 1.0 - f_b_cb;
   c.nT = in->n_T;
-  hc.lnkT.resize(c.nT);
-  hc.lnT.resize(c.nT);
-  double T0 = 0;
-  for (int i = 0; i < c.nT; i++) {
-    const double Ti = f_b_cb * in->Tb_T[i] + f_c_cb * in->Tc_T[i];
-    if (i == 0) T0 = Ti;
-    hc.lnkT[i] = std::log(in->k_T[i]);
-    hc.lnT[i] = std::log(Ti / T0);
+  c.n_z = in->n_z > 0 ? in->n_z : 0;
+  c.n_kb = c.n_z > 0 ? in->n_kb : 0;
+  const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
+  c.offT = (long long)off;
+  c.offLT = (long long)(off + nT);
+  c.offTb = (long long)(off + 2 * nT);
+  c.offA = (long long)(off + 3 * nT);
+  c.offKb = (long long)(off + 3 * nT + nz);
+  c.offTc = (long long)(off + 3 * nT + nz + nkb);
+  c.offB = (long long)(off + 3 * nT + nz + nkb + nz * nkb);
+  return hc;
+}
+// copy the caller's tables into the staging arena (raw; the device transforms them)
+static void stage_cosmology(const rtrg_cosmology *in, const Cosmo &c, double *base) {
+  const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
+  std::memcpy(base + c.offT, in->k_T, nT * sizeof(double));
+  std::memcpy(base + c.offLT, in->Tc_T, nT * sizeof(double));
+  std::memcpy(base + c.offTb, in->Tb_T, nT * sizeof(double));
+  for (size_t i = 0; i < nz; i++) base[c.offA + i] = 1.0 / (1.0 + in->z_interp[i]);
+  if (nz) {
+    std::memcpy(base + c.offKb, in->k_b, nkb * sizeof(double));
+    std::memcpy(base + c.offTc, in->Tc_b, nz * nkb * sizeof(double));
+    std::memcpy(base + c.offB, in->Tnu_b, nz * nkb * sizeof(double));
   }
-  // Beta table: f_nu T_nu / T_c on (a, k) (hdr:556-623)
-  c.n_z = in->n_z;
-  c.n_kb = in->n_z > 0 ? in->n_kb : 0;
-  const double fn = c.On / c.Om;
-  hc.anodes.resize(c.n_z);
-  for (int i = 0; i < c.n_z; i++) hc.anodes[i] = 1.0 / (1.0 + in->z_interp[i]);
-  if (c.n_z > 0) {
-    hc.kb.assign(in->k_b, in->k_b + c.n_kb);
-    hc.beta.resize((size_t)c.n_z * c.n_kb);
-    for (size_t i = 0; i < hc.beta.size(); i++) hc.beta[i] = fn * in->Tnu_b[i] / in->Tc_b[i];
+}
+
+int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *list) {
+  if (!h || n < 0 || (n > 0 && !list)) return fail(RTRG_EINVAL, "null argument");
+  size_t need = h->stage.used;
+  for (int i = 0; i < n; i++) {
+    int rc = check_cosmology(list[i]);
+    if (rc) return rc;
+    need += cosmology_doubles(list[i]);
   }
-  h->cos.push_back(std::move(hc));
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->stage.reserve(need) != RTRG_OK) return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", need * sizeof(double));
+  const size_t first = h->cos.size();
+  size_t off = h->stage.used;
+  for (int i = 0; i < n; i++) {
+    h->cos.push_back(describe_cosmology(list[i], off));
+    off += cosmology_doubles(list[i]);
+  }
+  h->stage.used = off;
+  // parallel staging: the copies are memory-bound, one thread saturates only ~10 GB/s
+  int nth = (int)std::thread::hardware_concurrency();
+  nth = std::max(1, std::min(std::min(nth, 16), n));
+  double *base = h->stage.base;
+  if (nth == 1) {
+    for (int i = 0; i < n; i++) stage_cosmology(list[i], h->cos[first + i].c, base);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++)
+      th.emplace_back([=]() {
+        for (int i = t; i < n; i += nth) stage_cosmology(list[i], h->cos[first + i].c, base);
+      });
+    for (auto &t : th) t.join();
+  }
   h->prepared = h->uploaded = false;
   return RTRG_OK;
 }
+
+int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) { return rtrg_add_cosmologies(h, 1, &in); }
 
 int rtrg_prepare(rtrg_handle *h) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   if (h->cos.empty()) return fail(RTRG_EINVAL, "no cosmologies");
   CU(cudaSetDevice(h->cfg.device));
-  free_pool(h->batch_allocs);
+  free_pool(h->batch_allocs);  // hook scratch buffers of the previous batch
   h->prepared = h->uploaded = false;
   const rtrg_config &cfg = h->cfg;
   const int B = (int)h->cos.size(), nk = cfg.nk, np = 4 * nk;
@@ -444,28 +540,19 @@ int rtrg_prepare(rtrg_handle *h) {
   S.k_lo = cfg.k_rank * rows_per;
   S.k_hi = S.k_lo + rows_per;
 
-  // --- pools + per-cosmology scalars
+  // --- per-cosmology scalars
   std::vector<Cosmo> cs(B);
-  std::vector<double> lnkT, lnT, anodes, kb, beta, zout((size_t)B * MAX_OUT, 0.0), aout((size_t)B * MAX_OUT, 1.0),
-      etaout((size_t)B * MAX_OUT, 0.0);
+  std::vector<double> zout((size_t)B * MAX_OUT, 0.0), aout((size_t)B * MAX_OUT, 1.0), etaout((size_t)B * MAX_OUT, 0.0);
   h->out_off.assign(B, 0);
   h->ncols.assign(B, 0);
   size_t off = 0;
-  int n_zmax = 2;
+  int n_zmax = 2, max_rows = 1;
   h->any_full = h->any_1loop = h->any_pr = false;
   for (int b = 0; b < B; b++) {
-    HostCosmo &hc = h->cos[b];
-    Cosmo c = hc.c;
-    c.offT = (long long)lnkT.size();
-    lnkT.insert(lnkT.end(), hc.lnkT.begin(), hc.lnkT.end());
-    lnT.insert(lnT.end(), hc.lnT.begin(), hc.lnT.end());
-    c.offA = (long long)anodes.size();
-    anodes.insert(anodes.end(), hc.anodes.begin(), hc.anodes.end());
-    c.offKb = (long long)kb.size();
-    kb.insert(kb.end(), hc.kb.begin(), hc.kb.end());
-    c.offB = (long long)beta.size();
-    beta.insert(beta.end(), hc.beta.begin(), hc.beta.end());
+    const HostCosmo &hc = h->cos[b];
+    const Cosmo &c = hc.c;
     n_zmax = std::max(n_zmax, c.n_z);
+    max_rows = std::max(max_rows, c.nT + c.n_z * c.n_kb);
     for (int i = 0; i < c.n_out; i++) {  // hdr:274-277
       const double z = hc.z_out[i], a = 1.0 / (1.0 + z);
       zout[(size_t)b * MAX_OUT + i] = z;
@@ -482,90 +569,127 @@ int rtrg_prepare(rtrg_handle *h) {
   }
   h->out_total = off;
   S.n_zmax = n_zmax;
-
-  auto &P = h->batch_allocs;
-  int rc = 0;
+  // growth-table axes (hdr:677-687)
+  std::vector<double> lna(cfg.n_lna + 1), lnkg(cfg.n_lnk + 1);
   {
-    const Cosmo *dc = nullptr;
-    rc = rc ? rc : dev_upload(P, &dc, cs);
-    S.cosmo = const_cast<Cosmo *>(dc);
-    const double *q = nullptr;
-    rc = rc ? rc : dev_upload(P, &q, zout), S.zout = const_cast<double *>(q);
-    rc = rc ? rc : dev_upload(P, &q, aout), S.aout = const_cast<double *>(q);
-    rc = rc ? rc : dev_upload(P, &q, etaout), S.etaout = const_cast<double *>(q);
-    rc = rc ? rc : dev_upload(P, &S.lnkT, lnkT);
-    rc = rc ? rc : dev_upload(P, &S.lnT, lnT);
-    rc = rc ? rc : dev_upload(P, &S.anodes, anodes);
-    rc = rc ? rc : dev_upload(P, &S.kb, kb);
-    rc = rc ? rc : dev_upload(P, &S.beta, beta);
-    // growth-table axes (hdr:677-687)
-    std::vector<double> lna(cfg.n_lna + 1), lnkg(cfg.n_lnk + 1);
     const double lna_min = std::log(GROWTH_A_MIN), dlna = std::log(GROWTH_A_MAX / GROWTH_A_MIN) / cfg.n_lna;
     const double lnk_min = std::log(GROWTH_K_MIN), dlnk = std::log(GROWTH_K_MAX / GROWTH_K_MIN) / cfg.n_lnk;
     for (int i = 0; i <= cfg.n_lna; i++) lna[i] = lna_min + dlna * i;
     for (int j = 0; j <= cfg.n_lnk; j++) lnkg[j] = lnk_min + dlnk * j;
-    rc = rc ? rc : dev_upload(P, &S.lna, lna);
-    rc = rc ? rc : dev_upload(P, &S.lnkg, lnkg);
-    std::vector<long long> oo(h->out_off);
-    const long long *dq = nullptr;
-    rc = rc ? rc : dev_upload(P, &dq, oo), S.out_off = const_cast<long long *>(dq);
-    const int *di = nullptr;
-    rc = rc ? rc : dev_upload(P, &di, h->ncols), S.ncols = const_cast<int *>(di);
   }
+
+  // --- carve the work arena (dry run for the size first)
   const size_t NE = (size_t)B * N_U * nk, ng = (size_t)(cfg.n_lna + 1) * (cfg.n_lnk + 1);
   const IntegralTabs &tb = h->tb;
-  rc = rc ? rc : dev_alloc(P, &S.bred, (size_t)B * n_zmax * S.nkk);
-  rc = rc ? rc : dev_alloc(P, &S.G, B * ng);
-  rc = rc ? rc : dev_alloc(P, &S.dD, B * ng);
-  rc = rc ? rc : dev_alloc(P, &S.Dnorm, (size_t)B * (cfg.n_lnk + 1));
-  rc = rc ? rc : dev_alloc(P, &S.Grow, (size_t)B * (cfg.n_lna + 1) * nk);
-  rc = rc ? rc : dev_alloc(P, &S.dDrow, (size_t)B * (cfg.n_lna + 1) * nk);
-  rc = rc ? rc : dev_alloc(P, &S.D0row, (size_t)B * nk);
-  rc = rc ? rc : dev_alloc(P, &S.Tgrid, (size_t)B * nk);
-  rc = rc ? rc : dev_alloc(P, &S.src_z1l, (size_t)B * N_SRC * nk);
-  rc = rc ? rc : dev_alloc(P, &S.D_z1l, (size_t)B * nk);
-  rc = rc ? rc : dev_alloc(P, &S.y_z1l, (size_t)B * 3 * nk);
-  rc = rc ? rc : dev_alloc(P, &S.y, NE);
-  rc = rc ? rc : dev_alloc(P, &S.ytmp, NE);
-  rc = rc ? rc : dev_alloc(P, &S.ynew, NE);
-  rc = rc ? rc : dev_alloc(P, &S.yerr, NE);
-  rc = rc ? rc : dev_alloc(P, &S.kst, RK_STAGES * NE);
-  rc = rc ? rc : dev_alloc(P, &h->d_yinit, NE);
-  rc = rc ? rc : dev_alloc(P, &S.src, (size_t)B * N_SRC * nk);
-  rc = rc ? rc : dev_alloc(P, &S.Prev, (size_t)B * 3 * tb.LP);
-  rc = rc ? rc : dev_alloc(P, &S.P3, (size_t)B * 3 * np);
-  rc = rc ? rc : dev_alloc(P, &S.Jpart, (size_t)B * N_JKERN * tb.nchunk * 9 * nk);
-  rc = rc ? rc : dev_alloc(P, &S.PZb, (size_t)B * N_ZKERN * 3 * nk);
-  rc = rc ? rc : dev_alloc(P, &S.Jlo, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.t, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.h, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.h_try, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.rmax_bits, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.i_out, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.flag_out, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.flag_step, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.flag_acc, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.final_step, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.done, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.m_full_step, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.m_full_acc, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.m_out_int, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &S.counters, (size_t)4 * B);
-  rc = rc ? rc : dev_alloc(P, &S.n_active, 1);
-  rc = rc ? rc : dev_alloc(P, &S.out, h->out_total);
-  rc = rc ? rc : dev_alloc(P, &S.hdr, (size_t)B * MAX_OUT * 5);
-  rc = rc ? rc : dev_alloc(P, &S.hdr0, (size_t)B * 2);
-  rc = rc ? rc : dev_alloc(P, &h->d_hookmask, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &h->d_minit, (size_t)B);
-  rc = rc ? rc : dev_alloc(P, &h->d_err, 1);
+  double *d_lna = nullptr, *d_lnkg = nullptr;
+  auto carve = [&](DeviceArena &A) {
+    A.used = 0;
+    S.cosmo = A.take<Cosmo>(B);
+    S.zout = A.take<double>((size_t)B * MAX_OUT);
+    S.aout = A.take<double>((size_t)B * MAX_OUT);
+    S.etaout = A.take<double>((size_t)B * MAX_OUT);
+    d_lna = A.take<double>(lna.size());
+    d_lnkg = A.take<double>(lnkg.size());
+    S.out_off = A.take<long long>(B);
+    S.ncols = A.take<int>(B);
+    h->d_T0 = A.take<double>(B);
+    S.bred = A.take<double>((size_t)B * n_zmax * S.nkk);
+    S.G = A.take<double>(B * ng);
+    S.dD = A.take<double>(B * ng);
+    S.Dnorm = A.take<double>((size_t)B * (cfg.n_lnk + 1));
+    S.Grow = A.take<double>((size_t)B * (cfg.n_lna + 1) * nk);
+    S.dDrow = A.take<double>((size_t)B * (cfg.n_lna + 1) * nk);
+    S.D0row = A.take<double>((size_t)B * nk);
+    S.Tgrid = A.take<double>((size_t)B * nk);
+    S.src_z1l = A.take<double>((size_t)B * N_SRC * nk);
+    S.D_z1l = A.take<double>((size_t)B * nk);
+    S.y_z1l = A.take<double>((size_t)B * 3 * nk);
+    S.y = A.take<double>(NE);
+    S.ytmp = A.take<double>(NE);
+    S.ynew = A.take<double>(NE);
+    S.yerr = A.take<double>(NE);
+    S.kst = A.take<double>(RK_STAGES * NE);
+    h->d_yinit = A.take<double>(NE);
+    S.src = A.take<double>((size_t)B * N_SRC * nk);
+    S.Prev = A.take<double>((size_t)B * 3 * tb.LP);
+    S.P3 = A.take<double>((size_t)B * 3 * np);
+    S.Jpart = A.take<double>((size_t)B * N_JKERN * tb.nchunk * 9 * nk);
+    S.PZb = A.take<double>((size_t)B * N_ZKERN * 3 * nk);
+    S.Jlo = A.take<double>(B);
+    S.t = A.take<double>(B);
+    S.h = A.take<double>(B);
+    S.h_try = A.take<double>(B);
+    S.rmax_bits = A.take<unsigned long long>(B);
+    S.i_out = A.take<int>(B);
+    S.flag_out = A.take<int>(B);
+    S.flag_step = A.take<int>(B);
+    S.flag_acc = A.take<int>(B);
+    S.final_step = A.take<int>(B);
+    S.done = A.take<int>(B);
+    S.m_full_step = A.take<int>(B);
+    S.m_full_acc = A.take<int>(B);
+    S.m_out_int = A.take<int>(B);
+    S.counters = A.take<long long>((size_t)4 * B);
+    S.n_active = A.take<int>(1);
+    S.out = A.take<double>(h->out_total);
+    S.hdr = A.take<double>((size_t)B * MAX_OUT * 5);
+    S.hdr0 = A.take<double>((size_t)B * 2);
+    h->d_hookmask = A.take<int>(B);
+    h->d_minit = A.take<int>(B);
+    h->d_err = A.take<int>(1);
+  };
+  {
+    DeviceArena dry;
+    carve(dry);
+    const size_t need = dry.used + 256;
+    if (need > h->work.cap) {
+      if (h->work.base) cudaFree(h->work.base);
+      h->work.base = nullptr;
+      h->work.cap = 0;
+      void *q = nullptr;
+      const size_t ncap = need + need / 8;
+      cudaError_t e = cudaMalloc(&q, ncap);
+      if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap, cudaGetErrorString(e));
+      h->work.base = (char *)q;
+      h->work.cap = ncap;
+    }
+    carve(h->work);
+  }
   h->d_raw = nullptr;
   h->d_scratch = nullptr;
   h->scratch_len = 0;
-  if (rc) {
-    free_pool(P);
-    return rc;
-  }
+  S.lna = d_lna;
+  S.lnkg = d_lnkg;
 
+  cudaStream_t st = h->stream;
+  // zero everything once (the Prev padding, the Q/I state rows ... rely on it)
+  CU(cudaMemsetAsync(h->work.base, 0, h->work.used, st));
+  // --- input pool: send the not yet uploaded tail of the staging arena
+  if (h->stage.used > h->d_in_cap) {
+    double *q = nullptr;
+    const size_t ncap = h->stage.used + h->stage.used / 8;
+    cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
+    if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
+    if (h->d_in) cudaFree(h->d_in);
+    h->d_in = q;
+    h->d_in_cap = ncap;
+    h->d_in_uploaded = 0;
+  }
+  // (the in-place transform below consumes the raw columns, so a re-prepare re-sends all)
+  h->d_in_uploaded = 0;
+  CU(cudaMemcpyAsync(h->d_in, h->stage.base, h->stage.used * sizeof(double), cudaMemcpyHostToDevice, st));
+  h->d_in_uploaded = h->stage.used;
+  S.in = h->d_in;
+  CU(cudaMemcpyAsync(S.cosmo, cs.data(), B * sizeof(Cosmo), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.zout, zout.data(), zout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.aout, aout.data(), aout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.etaout, etaout.data(), etaout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_lna, lna.data(), lna.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_lnkg, lnkg.data(), lnkg.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.out_off, h->out_off.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.ncols, h->ncols.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  h->launches += launch_prep_inputs(S, h->d_T0, max_rows, st, h->prof);
+  CU(cudaStreamSynchronize(st));  // the host vectors above go out of scope
   h->uploaded = true;
   return rtrg_device_init(h);
 }
@@ -713,7 +837,7 @@ int rtrg_set_profiling(rtrg_handle *h, int on) {
 int rtrg_profile_categories(void) { return PC_NCAT; }
 const char *rtrg_profile_name(int cat) {
   static const char *names[PC_NCAT] = {"k_extrap", "k_bilinear", "k_jlo", "k_pz", "k_assemble", "k_rhs",
-                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_beta_reduce",
+                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_prep_inputs", "k_beta_reduce",
                                        "k_growth_ode", "k_growth_tabs", "k_qag", "k_init_state"};
   return (cat >= 0 && cat < PC_NCAT) ? names[cat] : "";
 }

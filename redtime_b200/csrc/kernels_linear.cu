@@ -35,6 +35,43 @@ __device__ __forceinline__ double slot_k(const Batch &S, const double *kgrid, in
   return kk < S.nk ? kgrid[kk] : exp(S.lnkg[kk - S.nk]);
 }
 
+// In-place transform of the raw CAMB columns (once per upload):
+//   k_T -> ln k;  Tc_T -> ln(T_cb / T_cb[0]) with T_cb = f_b T_b + f_c T_c  (hdr:804-823)
+//   Tnu_b -> beta = f_nu T_nu / T_c                                          (hdr:556-623)
+__global__ void k_prep_T0(Batch S, double *__restrict__ T0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  const Cosmo &c = S.cosmo[b];
+  const double f_b = c.Ob / (c.Om - c.On), f_c = 1.0 - f_b;
+  T0[b] = f_b * S.in[c.offTb] + f_c * S.in[c.offLT];
+}
+__global__ void k_prep_inputs(Batch S, const double *__restrict__ T0) {
+  const int b = blockIdx.y;
+  const Cosmo &c = S.cosmo[b];
+  const double f_b = c.Ob / (c.Om - c.On), f_c = 1.0 - f_b, fn = c.On / c.Om, t0 = T0[b];
+  const long long nB = (long long)c.n_z * c.n_kb, n = c.nT + nB;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (i < c.nT) {
+      const double Ti = f_b * S.in[c.offTb + i] + f_c * S.in[c.offLT + i];
+      S.in[c.offT + i] = log(S.in[c.offT + i]);
+      S.in[c.offLT + i] = log(Ti / t0);
+    } else {
+      const long long j = i - c.nT;
+      S.in[c.offB + j] = fn * S.in[c.offB + j] / S.in[c.offTc + j];
+    }
+  }
+}
+int launch_prep_inputs(const Batch &S, double *T0, int max_rows, cudaStream_t st, Profiler *prof) {
+  RT_TIC(prof, PC_PREP_INPUTS, st);
+  k_prep_T0<<<(S.B + 127) / 128, 128, 0, st>>>(S, T0);
+  int bx = (max_rows + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  k_prep_inputs<<<dim3(bx, S.B), 256, 0, st>>>(S, T0);
+  RT_TOC(prof, st);
+  return 2;
+}
+
 __global__ void k_beta_reduce(Batch S, const double *__restrict__ kgrid) {
   const int b = blockIdx.y, kk = blockIdx.x * blockDim.x + threadIdx.x;
   if (kk >= S.nkk) return;

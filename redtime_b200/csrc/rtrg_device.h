@@ -13,6 +13,8 @@
 //                      Jpart  [B][14][nchunk][9][nk] partial bilinear sums
 //                      PZb    [B][7][3][nk]
 //                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
+//   inputs             in     [sum over cosmologies of 3 nT + n_z + n_kb + 2 n_z n_kb]
+//                                                    raw CAMB columns, transformed in place
 //   weight tables      Tc     [14][NUp][ldT]         compact circulant kernels (L2 resident)
 #pragma once
 #include "rtrg_math.h"
@@ -66,8 +68,8 @@ struct Batch {
   int k_lo, k_hi;  // k-rows owned by this rank (k-sharding); [0,nk) otherwise
   Cosmo *cosmo;            // [B]
   double *zout, *aout, *etaout;  // [B][MAX_OUT] output redshifts, 1/(1+z), ln(a/a_in)
-  // pooled input tables
-  const double *lnkT, *lnT, *anodes, *kb, *beta;
+  // pooled input tables (one buffer; per-cosmology offsets in Cosmo)
+  double *in;
   // linear-theory work
   double *bred;            // [B][n_zmax][nkk]
   const double *lna, *lnkg;// [n_lna+1], [n_lnk+1]
@@ -102,7 +104,7 @@ struct Batch {
 // numbers).  Off by default: a null Profiler* costs nothing.
 enum ProfCat {
   PC_EXTRAP, PC_BILINEAR, PC_JLO, PC_PZ, PC_ASSEMBLE, PC_RHS, PC_COMBINE, PC_FINAL, PC_CTRL,
-  PC_ACCEPT, PC_OUTPUT, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
+  PC_ACCEPT, PC_OUTPUT, PC_PREP_INPUTS, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
   PC_NCAT
 };
 #ifdef __CUDACC__
@@ -136,9 +138,9 @@ RT_HD BetaTab beta_tab(const Batch &S, const Cosmo &c) {
   BetaTab t;
   t.n_z = c.n_z;
   t.n_kb = c.n_kb;
-  t.a = S.anodes + c.offA;
-  t.k = S.kb + c.offKb;
-  t.beta = S.beta + c.offB;
+  t.a = S.in + c.offA;
+  t.k = S.in + c.offKb;
+  t.beta = S.in + c.offB;
   t.fn = c.On / c.Om;
   t.kmin = S.beta_kmin;
   t.kmax = S.beta_kmax;
@@ -161,8 +163,8 @@ RT_HD LinCtx lin_ctx(const Batch &S, int b) {
   L.c = &S.cosmo[b];
   L.bt = beta_tab(S, S.cosmo[b]);
   L.gt = growth_tab(S, b);
-  L.lnkT = S.lnkT + S.cosmo[b].offT;
-  L.lnT = S.lnT + S.cosmo[b].offT;
+  L.lnkT = S.in + S.cosmo[b].offT;
+  L.lnT = S.in + S.cosmo[b].offLT;
   L.nT = S.cosmo[b].nT;
   return L;
 }
