@@ -113,6 +113,24 @@ int rtrg_device_init(rtrg_handle *h);
  * out / hdr / hdr0 may be NULL: the tables then stay on the device (no D2H copy).     */
 int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *hdr0,
              int *status);
+/* ---- one high-resolution cosmology sharded over its k-rows ---------------
+ * Create one handle per rank with cfg.k_shards = number of ranks and cfg.k_rank = this rank
+ * (nk/8 must be divisible by k_shards), add the SAME cosmologies to each, attach a transport,
+ * then call rtrg_prepare / rtrg_run on every rank.  Before each integral evaluation the ranks
+ * all-gather their block of the three ln P_ab components (3*nk/k_shards doubles per rank),
+ * and after each RKF45 attempt they max-reduce the error norm, so all ranks replay the same
+ * accept/reject sequence; at the end every rank holds the complete output tables.
+ *   NCCL     : one process per GPU.  Rank 0 calls rtrg_kshard_nccl_id and ships the 128 bytes
+ *              to the others (MPI, torch.distributed, a file ...).
+ *   loopback : all ranks live in one process, each handle driven by its own host thread;
+ *              blocks move with peer copies (single-GPU testing, or NVLink P2P without NCCL). */
+int rtrg_kshard_nccl_id(char id[128]);
+int rtrg_kshard_init_nccl(rtrg_handle *h, const char id[128]);
+typedef struct rtrg_loopback rtrg_loopback;
+int rtrg_kshard_loopback_create(int nranks, rtrg_loopback **out);
+int rtrg_kshard_init_loopback(rtrg_handle *h, rtrg_loopback *g);
+void rtrg_kshard_loopback_free(rtrg_loopback *g);
+
 /* Work counters of the last rtrg_run for cosmology i:
  * counters[0]=RKF45 attempts, [1]=rejected, [2]=RHS evaluations, [3]=integral evaluations */
 int rtrg_counters(const rtrg_handle *h, int icosmo, long long counters[4]);

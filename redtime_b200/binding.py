@@ -72,6 +72,12 @@ def load_library():
     lib.rtrg_profile_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _dp]
     lib.rtrg_bench_dfma.argtypes = [C.c_int, C.c_double, _dp]
     lib.rtrg_bench_integrals.argtypes = [C.c_void_p, C.c_int]
+    lib.rtrg_kshard_nccl_id.argtypes = [C.c_char_p]
+    lib.rtrg_kshard_init_nccl.argtypes = [C.c_void_p, C.c_char_p]
+    lib.rtrg_kshard_loopback_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.rtrg_kshard_init_loopback.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rtrg_kshard_loopback_free.argtypes = [C.c_void_p]
+    lib.rtrg_kshard_loopback_free.restype = None
     lib.rtrg_run.argtypes = [C.c_void_p, _dp, C.c_size_t, _dp, _dp, _ip]
     lib.rtrg_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     lib.rtrg_extrap_P.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -194,6 +200,28 @@ def print_result(path, nk, out, hdr, hdr0, paramfile="params_redTime.dat"):
         libc.fclose(f)
 
 
+def kshard_nccl_id():
+    """128-byte NCCL unique id (call on rank 0, ship to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    _check(lib.rtrg_kshard_nccl_id(buf))
+    return buf.raw
+
+
+class LoopbackGroup:
+    """In-process transport of the k-sharded mode: one handle per rank, one host thread each."""
+
+    def __init__(self, nranks):
+        self.lib = load_library()
+        self.g = C.c_void_p()
+        _check(self.lib.rtrg_kshard_loopback_create(int(nranks), C.byref(self.g)))
+
+    def close(self):
+        if self.g:
+            self.lib.rtrg_kshard_loopback_free(self.g)
+            self.g = None
+
+
 def dfma_peak_tflops(device=0, seconds=0.5):
     """Measured FP64 FMA peak of the device (TFLOP/s)."""
     lib = load_library()
@@ -287,6 +315,12 @@ class RedTimeB200:
         status = np.zeros(self.n_cosmo, np.int32)
         _check(self.lib.rtrg_run(self.h, None, 0, None, None, status.ctypes.data_as(_ip)))
         return status
+
+    def kshard_init_nccl(self, unique_id):
+        _check(self.lib.rtrg_kshard_init_nccl(self.h, unique_id))
+
+    def kshard_init_loopback(self, group):
+        _check(self.lib.rtrg_kshard_init_loopback(self.h, group.g))
 
     def bench_integrals(self, reps=1):
         _check(self.lib.rtrg_bench_integrals(self.h, int(reps)))

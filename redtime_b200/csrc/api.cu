@@ -8,12 +8,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/redtime_b200.h"
 #include "fastpt_tables.h"
+#include "kshard.h"
 #include "rtrg_device.h"
 
 namespace rtrg {
@@ -135,6 +137,7 @@ struct rtrg_handle {
   double *d_yinit = nullptr, *d_raw = nullptr, *d_scratch = nullptr;
   int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
   size_t scratch_len = 0;
+  std::unique_ptr<Exchange> xch;  // k-shard transport (k_shards > 1)
   Profiler profiler;
   Profiler *prof = nullptr;  // &profiler when profiling is switched on
   double prof_ms[PC_NCAT] = {0};
@@ -749,6 +752,24 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   CU(cudaMemcpyAsync(S.n_active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
   const int with_jlo = h->cfg.print_bias;
 
+  // --- k-sharded mode: all-gather of the ranks' ln P rows, max-reduction of the error norm
+  const bool sharded = h->cfg.k_shards > 1;
+  if (sharded && (!h->xch || h->xch->nranks() != h->cfg.k_shards || h->xch->rank() != h->cfg.k_rank))
+    return fail(RTRG_EINVAL, "k_shards > 1 needs rtrg_kshard_init_nccl() or rtrg_kshard_init_loopback()");
+  const size_t rows_bytes = (size_t)(S.k_hi - S.k_lo) * sizeof(double);
+  std::string xerr;
+  auto gather_lnP = [&](double *yv) -> int {
+    if (!sharded) return 0;
+    std::vector<Segment> segs;
+    for (int b = 0; b < B; b++)
+      for (int c = 0; c < N_UP; c++) segs.push_back({yv + ((size_t)b * N_U + c) * nk, rows_bytes});
+    return h->xch->allgather(segs, st, &xerr);
+  };
+#define XCH(call)                                                             \
+  do {                                                                        \
+    if ((call) != 0) return fail(RTRG_ECUDA, "k-shard exchange: %s", xerr.c_str()); \
+  } while (0)
+
   // --- dydt_in of the first step
   if (h->any_full) {
     std::vector<int> m(B);
@@ -768,13 +789,16 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
     for (int s = 1; s < RK_STAGES; s++) {
       ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.flag_step, st));
+      if (h->any_full) XCH(gather_lnP(S.ytmp));
       if (h->any_full)
         h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, h->any_pr, 0, st, h->prof);
       ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st));
     }
     ODE_LAUNCH(PC_FINAL, launch_final(S, S.flag_step, st));
+    if (sharded) XCH(h->xch->allreduce_max_u64(S.rmax_bits, B, st, &xerr));
     ODE_LAUNCH(PC_CTRL, launch_ctrl_end(S, h->cfg.max_attempts, st));
     ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
+    XCH(gather_lnP(S.y));  // keep ln P of the accepted state complete on every rank
     if (h->any_full)
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, h->any_pr, 0, st, h->prof);
     ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st));
@@ -783,6 +807,14 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     rounds++;
   }
   CU(cudaGetLastError());
+  if (sharded) {  // every rank ends up with the complete tables
+    std::vector<Segment> segs;
+    for (int b = 0; b < B; b++)
+      for (int io = 0; io < h->cos[b].c.n_out; io++)
+        segs.push_back({S.out + h->out_off[b] + (size_t)io * nk * h->ncols[b], rows_bytes * h->ncols[b]});
+    XCH(h->xch->allgather(segs, st, &xerr));
+  }
+#undef XCH
 
   if (out) CU(cudaMemcpyAsync(out, S.out, h->out_total * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (hdr) CU(cudaMemcpyAsync(hdr, S.hdr, (size_t)B * MAX_OUT * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -812,6 +844,37 @@ int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
   return RTRG_OK;
 }
 long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
+
+int rtrg_kshard_nccl_id(char id[128]) {
+  std::string err;
+  if (!id) return fail(RTRG_EINVAL, "null argument");
+  if (nccl_unique_id(id, &err) != 0) return fail(RTRG_ECUDA, "%s", err.c_str());
+  return RTRG_OK;
+}
+int rtrg_kshard_init_nccl(rtrg_handle *h, const char id[128]) {
+  if (!h || !id) return fail(RTRG_EINVAL, "null argument");
+  if (h->cfg.k_shards < 2) return fail(RTRG_EINVAL, "handle was created with k_shards = %d", h->cfg.k_shards);
+  CU(cudaSetDevice(h->cfg.device));
+  std::string err;
+  h->xch = make_nccl_exchange(id, h->cfg.k_shards, h->cfg.k_rank, &err);
+  if (!h->xch) return fail(RTRG_ECUDA, "%s", err.c_str());
+  return RTRG_OK;
+}
+struct rtrg_loopback {
+  std::shared_ptr<LoopbackGroup> g;
+};
+int rtrg_kshard_loopback_create(int nranks, rtrg_loopback **out) {
+  if (nranks < 2 || !out) return fail(RTRG_EINVAL, "bad argument");
+  *out = new rtrg_loopback{make_loopback_group(nranks)};
+  return RTRG_OK;
+}
+int rtrg_kshard_init_loopback(rtrg_handle *h, rtrg_loopback *g) {
+  if (!h || !g) return fail(RTRG_EINVAL, "null argument");
+  if (h->cfg.k_shards < 2) return fail(RTRG_EINVAL, "handle was created with k_shards = %d", h->cfg.k_shards);
+  h->xch = make_loopback_exchange(g->g, h->cfg.k_rank, h->cfg.device);
+  return RTRG_OK;
+}
+void rtrg_kshard_loopback_free(rtrg_loopback *g) { delete g; }
 
 int rtrg_bench_integrals(rtrg_handle *h, int reps) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
