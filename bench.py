@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: concurrent processes (0 = host cores)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "kshard"],
+                    help="batch: cosmologies sharded over GPUs, no collective (headline); kshard: ONE "
+                         "high-accuracy nk=256 full Time-RG cosmology (BASELINE configs[2]) with its k rows "
+                         "sharded over the GPUs, NCCL all-gather of ln P_ab per RHS stage (strong scaling)")
     return ap.parse_args()
 
 
@@ -346,6 +350,122 @@ def run_b200(a, rank, world, local_rank):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------
+# k-sharded single cosmology (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------
+def run_kshard(a, rank, world, local_rank):
+    import gzip
+    import torch
+    import torch.distributed as dist
+    import redtime_b200 as rt
+    from redtime_b200 import workload as wl
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    steps = a.steps if a.steps is not None else 5
+    warm = max(a.warmup if a.warmup is not None else 3, 0)
+    nk = 256
+    c = wl.load_example1(a.subsample)
+    c["switches"] = [1, 0, 1, 1]
+    h = rt.RedTimeB200(device=local_rank, nk=nk, beta_kmin=1e-5, beta_kmax=20.0, n_lnk=1000, a_early=1e-50,
+                       k_shards=world, k_rank=rank)
+    stream = torch.cuda.Stream()
+    h.set_stream(stream.cuda_stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(rt.kshard_nccl_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        h.kshard_init_nccl(bytes(idt.cpu().numpy().tobytes()))
+    h.add_cosmology(c)
+    h.prepare()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        return h.run_resident()
+
+    for _ in range(warm):
+        step()
+    clocks = ClockSampler(local_rank)
+    h.set_profiling(True)
+    l0 = h.launch_count()
+    sync_all()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    sync_all()
+    clk = clocks.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = h.launch_count() - l0
+    prof = h.profile()
+    h.set_profiling(False)
+    cnt = h.counters(0)
+    # end to end: host buffers in, tables out (every rank ends with the full tables)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h.clear()
+        h.add_cosmology(c)
+        h.prepare()
+        tables, hdr, hdr0, status = h.run()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    if rank != 0:
+        return
+    n_out = tables[0].shape[0]
+    # parity against the committed oracle output of the same configuration
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "example1_oracle_hiacc_full.dat.gz"), "rt") as f:
+        ref = np.array([l.split() for l in f.read().split("\n") if l.strip() and not l.startswith("#")], dtype=float)
+    ref = ref.reshape(tables[0].shape)
+    err = np.max(np.abs(tables[0] - ref) / (np.abs(ref) + 1e-300), axis=(0, 1)) if a.subsample == 1 else None
+    grid = rt.grid_info(nk)
+    flop_eval = flops_per_integral_eval(grid, True, nk)
+    n_bil, ms_bil = prof["k_bilinear"]
+    peak = rt.dfma_peak_tflops(local_rank, 0.5)
+    achieved = flop_eval / world * cnt["integral_evals"] * steps / (ms_bil * 1e-3) * 1e-12 if ms_bil else 0.0
+    line = {"metric": "cosmology*redshift outputs/sec, ONE nk=256 high-accuracy full-TRG cosmology, k-sharded",
+            "value": n_out * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "example-1 CAMB tables (the reference's examples/1_redTime)",
+            "config": {"workload": "BASELINE configs[2]: single cosmology, nk=256, beta clamp [1e-5,20], n_lnk=1000, "
+                                   "a_early=1e-50, switches 1 0 1 1, k rows sharded over %d GPU(s), NCCL all-gather of "
+                                   "ln P_ab per RHS stage + max-reduce of the error norm per attempt" % world,
+                       "l2": "256 MiB flush before every step"},
+            "clocks": clk,
+            "e2e": {"value": n_out * steps / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / steps,
+                    "h2d_bytes_per_step": int(c["k_T"].nbytes * 3 + c["k_b"].nbytes + c["Tc_b"].nbytes * 2),
+                    "d2h_bytes_per_step": int(tables[0].nbytes)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "k_bilinear", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "launches": n_bil,
+                         "avg_launch_ms": ms_bil / max(n_bil, 1), "share_of_step": ms_bil / ms},
+            "counters": cnt,
+            "parity_max_rel_err_cols_1_10_vs_oracle": None if err is None else float(err[:10].max()),
+            "kernel_ms_in_timed_region": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in prof.items() if v[0]}}
+    print(json.dumps(line))
+
+
 def main():
     a = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -359,7 +479,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29517"] + sys.argv
         sys.exit(subprocess.call(cmd))
-    run_b200(a, rank, world, local_rank)
+    if a.workload == "kshard":
+        run_kshard(a, rank, world, local_rank)
+    else:
+        run_b200(a, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
