@@ -212,14 +212,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # this library
 # ------------------------------------------------------------------------------------------
-def flops_per_integral_eval(grid, with_jn0, nk):
-    """Algorithmic FLOP of ONE evaluation of the mode-coupling integrals for one cosmology in
-    the factored form the kernel uses: per bilinear kernel n, for each of the nk
-    rows and 3 beta-side spectra an nsup x nsup matrix-vector product (2 nsup^2 FLOP), then 9
-    alpha-side dot products (2 nsup)."""
+def flops_per_matvec_set(grid, nk):
+    """Algorithmic FLOP of one (kernel n, beta-side spectrum) set of k_bilinear for one
+    cosmology: for each of the nk rows an nsup x nsup matrix-vector product
+    (2 nsup^2 FLOP), then 3 alpha-side dot products (2 nsup each).  A full evaluation of all
+    outputs is 42 sets; the library computes only the sets the requested outputs consume."""
     nsup = grid["nsup"]
-    nkern = 14 if with_jn0 else 7
-    return nkern * nk * (3 * 2.0 * nsup * nsup + 9 * 2.0 * nsup)
+    return nk * (2.0 * nsup * nsup + 3 * 2.0 * nsup)
 
 
 def run_b200(a, rank, world, local_rank):
@@ -300,6 +299,7 @@ def run_b200(a, rank, world, local_rank):
     prof = h.profile()
     h.set_profiling(False)
     evals = sum(h.counters(i)["integral_evals"] for i in range(B))  # per step (last run)
+    sets = sum(h.matvec_sets(i) for i in range(B))                  # per step (device_init + run)
     value = world * outputs_per_step * steps / (ms_total * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers
@@ -325,8 +325,8 @@ def run_b200(a, rank, world, local_rank):
     # ---- roofline of the dominant kernel
     grid = rt.grid_info(NK)
     n_bil, ms_bil = prof["k_bilinear"]
-    flop_eval = flops_per_integral_eval(grid, True, NK)
-    flop_total = flop_eval * evals * steps
+    flop_set = flops_per_matvec_set(grid, NK)
+    flop_total = flop_set * sets * steps
     peak = rt.dfma_peak_tflops(local_rank, 0.5)
     achieved = flop_total / (ms_bil * 1e-3) * 1e-12 if ms_bil > 0 else 0.0
     sm_clk = 1.965e9
@@ -335,7 +335,8 @@ def run_b200(a, rank, world, local_rank):
             "peak_source": "DFMA loop measured live by rtrg_bench_dfma (MEASURED_PEAKS.json has no FP64 figure); "
                            "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = %.1f TFLOP/s" % (148 * 64 * 2 * sm_clk * 1e-12),
             "launches": n_bil, "avg_launch_ms": ms_bil / max(n_bil, 1),
-            "algorithmic_flop_per_integral_evaluation": flop_eval, "integral_evaluations_per_step": evals,
+            "algorithmic_flop_per_matvec_set": flop_set, "matvec_sets_per_step": sets,
+            "integral_evaluations_per_step": evals,
             "share_of_step": ms_bil / ms_total}
     kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in prof.items() if v[0]}
     cpu = None if a.no_cpu_baseline else cpu_baseline(a)
@@ -440,10 +441,10 @@ def run_kshard(a, rank, world, local_rank):
     ref = ref.reshape(tables[0].shape)
     err = np.max(np.abs(tables[0] - ref) / (np.abs(ref) + 1e-300), axis=(0, 1)) if a.subsample == 1 else None
     grid = rt.grid_info(nk)
-    flop_eval = flops_per_integral_eval(grid, True, nk)
     n_bil, ms_bil = prof["k_bilinear"]
     peak = rt.dfma_peak_tflops(local_rank, 0.5)
-    achieved = flop_eval / world * cnt["integral_evals"] * steps / (ms_bil * 1e-3) * 1e-12 if ms_bil else 0.0
+    # this rank's share: matvec sets x its nk/world rows
+    achieved = flops_per_matvec_set(grid, nk) / world * h.matvec_sets(0) * steps / (ms_bil * 1e-3) * 1e-12 if ms_bil else 0.0
     line = {"metric": "cosmology*redshift outputs/sec, ONE nk=256 high-accuracy full-TRG cosmology, k-sharded",
             "value": n_out * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -134,6 +134,10 @@ void rtrg_kshard_loopback_free(rtrg_loopback *g);
 /* Work counters of the last rtrg_run for cosmology i:
  * counters[0]=RKF45 attempts, [1]=rejected, [2]=RHS evaluations, [3]=integral evaluations */
 int rtrg_counters(const rtrg_handle *h, int icosmo, long long counters[4]);
+/* (kernel, beta-side spectrum) matrix-vector sets k_bilinear executed for cosmology i since the
+ * last rtrg_device_init, up to the end of the last rtrg_run; one set = nk rows x (2 nsup^2 +
+ * 6 nsup) FLOP.  Only the products the requested outputs consume are computed.            */
+long long rtrg_matvec_sets(const rtrg_handle *h, int icosmo);
 /* number of kernel launches issued by this handle so far */
 long long rtrg_launch_count(const rtrg_handle *h);
 /* Per-kernel device timing (CUDA events on the launching stream), off by default.

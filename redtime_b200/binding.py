@@ -55,6 +55,8 @@ def load_library():
     lib.rtrg_version.restype = C.c_char_p
     lib.rtrg_launch_count.restype = C.c_longlong
     lib.rtrg_launch_count.argtypes = [C.c_void_p]
+    lib.rtrg_matvec_sets.restype = C.c_longlong
+    lib.rtrg_matvec_sets.argtypes = [C.c_void_p, C.c_int]
     lib.rtrg_default_config.argtypes = [C.POINTER(Config)]
     lib.rtrg_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.rtrg_destroy.argtypes = [C.c_void_p]
@@ -359,6 +361,9 @@ class RedTimeB200:
         c = (C.c_longlong * 4)()
         _check(self.lib.rtrg_counters(self.h, i, c))
         return dict(attempts=c[0], rejected=c[1], rhs=c[2], integral_evals=c[3])
+
+    def matvec_sets(self, i=0):
+        return int(self.lib.rtrg_matvec_sets(self.h, i))
 
     def launch_count(self):
         return int(self.lib.rtrg_launch_count(self.h))

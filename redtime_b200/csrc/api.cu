@@ -21,7 +21,7 @@
 namespace rtrg {
 // kernels_integrals.cu
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
-                     double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
+                     double *src, double *raw, const int *mask, int groups, int identical,
                      cudaStream_t st, Profiler *prof);
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st);
@@ -130,7 +130,7 @@ struct rtrg_handle {
   Batch S;
   bool prepared = false, uploaded = false;
   long long launches = 0;
-  std::vector<long long> out_off, counters;
+  std::vector<long long> out_off, counters, matvecs;
   std::vector<int> ncols;
   size_t out_total = 0;
   bool any_full = false, any_1loop = false, any_pr = false;
@@ -152,6 +152,14 @@ struct rtrg_handle {
     RT_TOC(h->prof, st);             \
     h->launches++;                   \
   } while (0)
+
+// Output groups an evaluation has to deliver (see assembly need table):
+//   inside the RHS / for the z1l cache: A, and R when some cosmology evolves Q (rt:1516)
+//   at an output redshift in 1-loop mode (rt:1646): what the printed columns consume
+static int grp_rhs(const rtrg_handle *h) { return GRP_A | ((h->cfg.print_Q || h->any_pr) ? GRP_R : 0); }
+static int grp_out(const rtrg_handle *h) {
+  return (h->any_pr ? GRP_PT : 0) | (h->cfg.print_A ? GRP_A : 0) | ((h->cfg.print_bias && h->any_pr) ? GRP_PMR : 0);
+}
 
 // fold the recorded events into the per-category totals (stream must be idle)
 static void prof_collect(rtrg_handle *h) {
@@ -373,6 +381,14 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   }
   for (int r = 0; r < N_SRC; r++) t_start[r + 1] += t_start[r];
   tb.n_terms = (int)terms.size();
+  // which (kernel, beta-side spectrum) products each output group consumes
+  std::memset(tb.need_cd, 0, sizeof tb.need_cd);
+  for (const AsmTerm &t : terms) {
+    if (t.src != 0 && t.src != 2) continue;  // J (kernels 0-6) and Jn0 (7-13)
+    const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
+    const int n = t.index / 9 + (t.src == 2 ? 7 : 0), cd = t.index % 3;
+    tb.need_cd[gi][n] |= (unsigned char)(1 << cd);
+  }
 
   int rc = 0;
   auto &P = h->table_allocs;
@@ -633,6 +649,7 @@ int rtrg_prepare(rtrg_handle *h) {
     S.m_full_acc = A.take<int>(B);
     S.m_out_int = A.take<int>(B);
     S.counters = A.take<long long>((size_t)4 * B);
+    S.matvecs = A.take<long long>(B);
     S.n_active = A.take<int>(1);
     S.out = A.take<double>(h->out_total);
     S.hdr = A.take<double>((size_t)B * MAX_OUT * 5);
@@ -708,6 +725,7 @@ int rtrg_device_init(rtrg_handle *h) {
   const int B = S.B, nk = S.nk;
   const size_t NE = (size_t)B * N_U * nk;
   cudaStream_t st = h->stream;
+  CU(cudaMemsetAsync(S.matvecs, 0, B * sizeof(long long), st));
   h->launches += launch_linear_init(S, h->d_kgrid, st, h->prof);
   CU(cudaMemcpyAsync(h->d_yinit, S.y, NE * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (h->any_1loop) {
@@ -715,8 +733,8 @@ int rtrg_device_init(rtrg_handle *h) {
     std::vector<int> m(B);
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->launches += launch_integrals(tb, S, S.y_z1l, 3LL * nk, S.src_z1l, nullptr, h->d_minit, h->any_pr,
-                                    cfg.print_bias, st, h->prof);
+    h->launches += launch_integrals(tb, S, S.y_z1l, 3LL * nk, S.src_z1l, nullptr, h->d_minit, grp_rhs(h),
+                                    /*identical=*/1, st, h->prof);
   }
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
@@ -750,7 +768,6 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   CU(cudaMemsetAsync(S.done, 0, B * sizeof(int), st));
   CU(cudaMemsetAsync(S.counters, 0, 4 * B * sizeof(long long), st));
   CU(cudaMemcpyAsync(S.n_active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
-  const int with_jlo = h->cfg.print_bias;
 
   // --- k-sharded mode: all-gather of the ranks' ln P rows, max-reduction of the error norm
   const bool sharded = h->cfg.k_shards > 1;
@@ -775,7 +792,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     std::vector<int> m(B);
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, h->any_pr, 0, st, h->prof);
+    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof);
   }
   ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st));
 
@@ -784,14 +801,14 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
   while (n_active > 0 && rounds < max_rounds) {
     ODE_LAUNCH(PC_CTRL, launch_ctrl_begin(S, st));
-    if (h->any_1loop)
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, h->any_pr, with_jlo, st, h->prof);
+    if (h->any_1loop && grp_out(h))
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, grp_out(h), 0, st, h->prof);
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
     for (int s = 1; s < RK_STAGES; s++) {
       ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.flag_step, st));
       if (h->any_full) XCH(gather_lnP(S.ytmp));
       if (h->any_full)
-        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, h->any_pr, 0, st, h->prof);
+        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, grp_rhs(h), 0, st, h->prof);
       ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st));
     }
     ODE_LAUNCH(PC_FINAL, launch_final(S, S.flag_step, st));
@@ -800,7 +817,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
     XCH(gather_lnP(S.y));  // keep ln P of the accepted state complete on every rank
     if (h->any_full)
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, h->any_pr, 0, st, h->prof);
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof);
     ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st));
     CU(cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -820,7 +837,9 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   if (hdr) CU(cudaMemcpyAsync(hdr, S.hdr, (size_t)B * MAX_OUT * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (hdr0) CU(cudaMemcpyAsync(hdr0, S.hdr0, (size_t)B * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   h->counters.assign((size_t)4 * B, 0);
+  h->matvecs.assign(B, 0);
   CU(cudaMemcpyAsync(h->counters.data(), S.counters, 4 * B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->matvecs.data(), S.matvecs, B * sizeof(long long), cudaMemcpyDeviceToHost, st));
   std::vector<Cosmo> cs(B);
   CU(cudaMemcpyAsync(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -844,6 +863,10 @@ int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
   return RTRG_OK;
 }
 long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
+long long rtrg_matvec_sets(const rtrg_handle *h, int i) {
+  if (!h || i < 0 || (size_t)i >= h->matvecs.size()) return -1;
+  return h->matvecs[i];
+}
 
 int rtrg_kshard_nccl_id(char id[128]) {
   std::string err;
@@ -882,8 +905,8 @@ int rtrg_bench_integrals(rtrg_handle *h, int reps) {
   CU(cudaSetDevice(h->cfg.device));
   const int nk = h->S.nk;
   for (int r = 0; r < reps; r++)
-    h->launches += launch_integrals(h->tb, h->S, h->S.y_z1l, 3LL * nk, h->S.src, nullptr, nullptr, 1,
-                                    h->cfg.print_bias, h->stream, h->prof);
+    h->launches += launch_integrals(h->tb, h->S, h->S.y_z1l, 3LL * nk, h->S.src, nullptr, nullptr, GRP_ALL, 0,
+                                    h->stream, h->prof);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   prof_collect(h);
@@ -963,7 +986,7 @@ static int run_integrals_hook(rtrg_handle *h, int icosmo, const double *lnP3nk, 
   double *yslot = h->S.ytmp + (size_t)icosmo * N_U * nk;
   CU(cudaMemcpyAsync(yslot, lnP3nk, 3 * nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)N_U * nk, h->S.src, want_raw ? h->d_raw : nullptr,
-                                  h->d_hookmask, h->cos[icosmo].c.sw_pr, 1, h->stream, nullptr);
+                                  h->d_hookmask, GRP_ALL, 0, h->stream, nullptr);
   return RTRG_OK;
 }
 
@@ -1025,7 +1048,7 @@ int rtrg_derivatives(rtrg_handle *h, int icosmo, double eta, const double *y, do
   CU(cudaMemcpyAsync(h->S.t + icosmo, &eta, sizeof(double), cudaMemcpyHostToDevice, st));
   const Cosmo &c = h->cos[icosmo].c;
   if (c.sw_nl && !c.sw_1l)
-    h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)n, h->S.src, nullptr, h->d_hookmask, c.sw_pr, 0, st, nullptr);
+    h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)n, h->S.src, nullptr, h->d_hookmask, grp_rhs(h), 0, st, nullptr);
   launch_rhs(h->S, h->d_kgrid, h->S.ytmp, h->S.ynew, -1, h->d_hookmask, st), h->launches++;
   CU(cudaMemcpyAsync(dy, h->S.ynew + (size_t)icosmo * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -68,11 +68,12 @@ __device__ __forceinline__ double warp_sum(double x) {
 __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
                          const double *__restrict__ y, long long ystride,
                          double *__restrict__ P3, double *__restrict__ Prev,
-                         const int *__restrict__ mask) {
+                         const int *__restrict__ mask, long long *__restrict__ matvecs, int units) {
   const int b = blockIdx.y;
   if (mask && !mask[b]) return;
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= tb.np) return;
+  if (ip == 0 && matvecs) matvecs[b] += units;  // one launch at a time per stream: no race
   const double *yb = y + (long long)b * ystride;
   const int n0 = tb.ex_n0[ip];
   const double w0 = tb.ex_w[4 * ip], w1 = tb.ex_w[4 * ip + 1], w2 = tb.ex_w[4 * ip + 2],
@@ -120,15 +121,31 @@ __device__ __forceinline__ void warp_sum_multi(double (&v)[V], int lane) {
   }
 }
 
+// One work item of a k_bilinear launch: kernel n applied to the beta-side spectra cd[0..NCD).
+// Only the (kernel, spectrum) combinations the requested outputs consume are computed
+// (assembly_needs): e.g. the RHS needs A and R = all of J but only 3 of the 7 Jn0 kernels,
+// the default output columns need P_T,jm = 12 kernels x 2 spectra.  replicate: the three
+// spectra are identical (1-loop cache at z1l, rt:1303-1305), one product serves all 9 pairs.
+struct BilItem {
+  short n, cd[3];
+};
+struct BilLaunch {
+  BilItem it[N_JKERN];
+  int replicate;
+};
+
 // R: output rows per CTA; TPB: threads (one alpha-side lag each); MINB: CTAs per SM the
-// register budget is tuned for; VC: beta-side lags per software-pipelined chunk.
-template <int R, int TPB, int MINB, int VC>
+// register budget is tuned for; VC: beta-side lags per software-pipelined chunk; NCD: number of
+// beta-side spectra of every item of this launch.
+template <int R, int TPB, int MINB, int VC, int NCD>
 __global__ void __launch_bounds__(TPB, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
-               double *__restrict__ Jpart, int n_first, int row0, const int *__restrict__ mask) {
+               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int row0,
+               const int *__restrict__ mask) {
   const int e = blockIdx.z;
   if (mask && !mask[e]) return;
-  const int n = n_first + blockIdx.y;
+  const BilItem item = L.it[blockIdx.y];
+  const int n = item.n;
   if (n >= 7 && !cosmo[e].sw_pr) return;  // Jn0 only feeds the RSD terms (rt:804)
   const int rb = blockIdx.x / tb.nchunk, chunk = blockIdx.x - rb * tb.nchunk;
   extern __shared__ __align__(128) double sm[];
@@ -151,10 +168,15 @@ __global__ void __launch_bounds__(TPB, MINB)
   const bool active = tu < tb.NV;
   const int tuc = active ? tu : tb.NV - 1;
   const double *Tp = tb.Tc + ((size_t)n * tb.NUp + i0) * ldT + i0 + tuc;
-
-  double acc[R][3];
+  const double *s_c[NCD];
 #pragma unroll
-  for (int r = 0; r < R; r++) acc[r][0] = acc[r][1] = acc[r][2] = 0.0;
+  for (int c = 0; c < NCD; c++) s_c[c] = s_a + item.cd[c] * LP;
+
+  double acc[R][NCD];
+#pragma unroll
+  for (int r = 0; r < R; r++)
+#pragma unroll
+    for (int c = 0; c < NCD; c++) acc[r][c] = 0.0;
   double tcur[VC], tnxt[VC];
 #pragma unroll
   for (int s = 0; s < VC; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
@@ -170,10 +192,10 @@ __global__ void __launch_bounds__(TPB, MINB)
       for (int s = 0; s < VC; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < NCD; c++) {
       // window w[q] = arev_c[tv0 + q - (R-1)], q in [0, VC+R-1): 16-byte broadcast loads
       double w[2 * NW];
-      const double2 *wp = reinterpret_cast<const double2 *>(s_a + c * LP + tv0);
+      const double2 *wp = reinterpret_cast<const double2 *>(s_c[c] + tv0);
 #pragma unroll
       for (int q = 0; q < NW; q++) {
         const double2 v = wp[q];
@@ -189,30 +211,38 @@ __global__ void __launch_bounds__(TPB, MINB)
     for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
   }
 
-  // alpha side: out[ab][cd][r] = sum_u arev_ab[u - r] * S_u[r][cd].  Eight rows at a time go
+  // alpha side: out[ab][c][r] = sum_u arev_ab[u - r] * S_u[r][c].  Eight rows at a time go
   // through the halving reduction; lane 4*r then holds row r.
   static_assert(R == 8, "the epilogue reduction is written for 8 rows per CTA");
-#pragma unroll
-  for (int ab = 0; ab < 3; ab++) {
+  const int nab = L.replicate ? 1 : 3;
+  for (int ab = 0; ab < nab; ab++) {
     double m[R];
 #pragma unroll
     for (int r = 0; r < R; r++) m[r] = active ? s_a[ab * LP + (R - 1) + tu - r] : 0.0;
 #pragma unroll
-    for (int cd = 0; cd < 3; cd++) {
+    for (int c = 0; c < NCD; c++) {
       double prod[R];
 #pragma unroll
-      for (int r = 0; r < R; r++) prod[r] = m[r] * acc[r][cd];
+      for (int r = 0; r < R; r++) prod[r] = m[r] * acc[r][c];
       warp_sum_multi<R>(prod, lane);
-      if ((lane & 3) == 0) s_red[warp * (9 * R) + (ab * 3 + cd) * R + (lane >> 2)] = prod[0];
+      if ((lane & 3) == 0) s_red[warp * (9 * R) + (ab * 3 + c) * R + (lane >> 2)] = prod[0];
     }
   }
   __syncthreads();
   if (tid < 9 * R) {
-    double s = 0.0;
+    const int slot = tid / R, r = tid - slot * R, ab = slot / 3, c = slot - 3 * ab;
+    if (ab < nab && c < NCD) {
+      double s = 0.0;
 #pragma unroll 1
-    for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
-    const int pair = tid / R, r = tid - pair * R;
-    Jpart[((((long long)e * N_JKERN + n) * tb.nchunk + chunk) * 9 + pair) * tb.nk + i0 + r] = s;
+      for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
+      double *dst = Jpart + (((long long)e * N_JKERN + n) * tb.nchunk + chunk) * 9 * tb.nk + i0 + r;
+      if (L.replicate) {
+#pragma unroll
+        for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
+      } else {
+        dst[(long long)(ab * 3 + item.cd[c]) * tb.nk] = s;
+      }
+    }
   }
 }
 
@@ -282,7 +312,7 @@ __global__ void __launch_bounds__(256)
     k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
                const double *__restrict__ PZb, const double *__restrict__ P3,
                const double *__restrict__ Jlo, double *__restrict__ src, double *__restrict__ raw,
-               int row0, int nrows, const int *__restrict__ mask) {
+               int row0, int nrows, const int *__restrict__ mask, int groups) {
   const int e = blockIdx.y;
   if (mask && !mask[e]) return;
   __shared__ double vals[ASM_NV][ASM_ROWS + 1];
@@ -320,6 +350,10 @@ __global__ void __launch_bounds__(256)
   for (int idx = tid; idx < N_SRC * ASM_ROWS; idx += blockDim.x) {
     const int o = idx / ASM_ROWS, rr = idx - o * ASM_ROWS;
     if (rr >= rows) continue;
+    // output groups: A rows 0-13, R 14-37, P_T,jm 38-46, P_MR,n 47-54; rows of groups that
+    // were not requested keep their old content (their inputs were not computed)
+    const int grp = o < 14 ? GRP_A : o < 38 ? GRP_R : o < 47 ? GRP_PT : GRP_PMR;
+    if (!(groups & grp)) continue;
     const int i = r0 + rr;
     const double k = tb.kgrid[i], kinv = 1.0 / k;
     double acc = 0.0;
@@ -335,47 +369,67 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------- launchers
 enum { BIL_TPB = 352 };
-// kernel variant (tuning knob, RTRG_BIL_VARIANT): 0 = 2 CTAs/SM, 8-lag chunks (default);
-// 1 = 1 CTA/SM, 8-lag chunks; 2 = 2 CTAs/SM, 4-lag chunks
+// kernel variant (tuning knob, RTRG_BIL_VARIANT): 0 = 2 CTAs/SM (default); 1 = 1 CTA/SM
 static int g_bil_variant = 0;
 
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
   return (size_t)(3 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
 }
 
-// Full evaluation for every (unmasked) cosmology: y -> src (and optionally raw J/PZ/Jn0).
-// Returns the number of kernel launches.
+template <int NCD>
+static void launch_bilinear_class(const IntegralTabs &tb, const Batch &S, const BilLaunch &L, int nitems, int row0,
+                                  int nrows, const int *mask, cudaStream_t st) {
+  if (nitems == 0) return;
+  dim3 g((nrows / BIL_R) * tb.nchunk, nitems, S.B);
+  const size_t smem = bilinear_smem_bytes(tb);
+  if (NCD == 3 && g_bil_variant == 1)
+    k_bilinear<BIL_R, BIL_TPB, 1, 8, 3><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
+  else
+    k_bilinear<BIL_R, BIL_TPB, 2, 8, NCD><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
+}
+
+// Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
+// groups (GRP_* bits; GRP_ALL also fills raw J/PZ/Jn0 when raw != nullptr).  identical != 0:
+// the three spectra in y are the same array (1-loop cache).  Returns the number of launches.
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
-                     double *src, double *raw, const int *mask, int with_jn0, int with_jlo,
+                     double *src, double *raw, const int *mask, int groups, int identical,
                      cudaStream_t st, Profiler *prof) {
   const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
   int launches = 0;
+  // work items by number of beta-side spectra
+  BilLaunch L[3];
+  int nit[3] = {0, 0, 0};
+  int units = 0;
+  for (int n = 0; n < N_JKERN; n++) {
+    int need = 0;
+    for (int gi = 0; gi < 4; gi++)
+      if (groups & (1 << gi)) need |= tb.need_cd[gi][n];
+    if (!need) continue;
+    if (identical) need = 1;
+    BilItem it;
+    it.n = (short)n;
+    int ncd = 0;
+    for (int c = 0; c < 3; c++)
+      if (need & (1 << c)) it.cd[ncd++] = (short)c;
+    for (int c = ncd; c < 3; c++) it.cd[c] = 0;
+    L[ncd - 1].it[nit[ncd - 1]++] = it;
+    units += ncd;
+  }
+  for (int c = 0; c < 3; c++) L[c].replicate = identical ? 1 : 0;
   {
     dim3 g((tb.np + 127) / 128, B);
     RT_TIC(prof, PC_EXTRAP, st);
-    k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask);
+    k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, S.matvecs, units);
     RT_TOC(prof, st);
     launches++;
   }
-  {
-    const int nkern = with_jn0 ? N_JKERN : 7;
-    dim3 g((nrows / BIL_R) * tb.nchunk, nkern, B);
-    RT_TIC(prof, PC_BILINEAR, st);
-    const size_t smem = bilinear_smem_bytes(tb);
-    switch (g_bil_variant) {
-      case 1:
-        k_bilinear<BIL_R, BIL_TPB, 1, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
-        break;
-      case 2:
-        k_bilinear<BIL_R, BIL_TPB, 2, 4><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
-        break;
-      default:
-        k_bilinear<BIL_R, BIL_TPB, 2, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, 0, row0, mask);
-    }
-    RT_TOC(prof, st);
-    launches++;
-  }
-  if (with_jlo) {
+  RT_TIC(prof, PC_BILINEAR, st);
+  launch_bilinear_class<1>(tb, S, L[0], nit[0], row0, nrows, mask, st);
+  launch_bilinear_class<2>(tb, S, L[1], nit[1], row0, nrows, mask, st);
+  launch_bilinear_class<3>(tb, S, L[2], nit[2], row0, nrows, mask, st);
+  RT_TOC(prof, st);
+  launches += (nit[0] > 0) + (nit[1] > 0) + (nit[2] > 0);
+  if (groups & GRP_PMR) {
     RT_TIC(prof, PC_JLO, st);
     k_jlo<<<B, 256, tb.nsup * sizeof(double), st>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
     RT_TOC(prof, st);
@@ -393,7 +447,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     dim3 g((nrows + ASM_ROWS - 1) / ASM_ROWS, B);
     RT_TIC(prof, PC_ASSEMBLE, st);
     k_assemble<<<g, 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
-                                  nrows, mask);
+                                  nrows, mask, groups);
     RT_TOC(prof, st);
     launches++;
   }
@@ -403,17 +457,18 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st) {
   dim3 g((tb.np + 127) / 128, S.B);
-  k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask);
+  k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, nullptr, 0);
 }
 
 int integrals_configure() {
   const char *v = getenv("RTRG_BIL_VARIANT");
   g_bil_variant = (v && *v) ? atoi(v) : 0;
   // opt in to the dynamic shared memory the bilinear kernel may need for large grids
-  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  const int sm = 96 * 1024;
+  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 1, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
 }
 
 }  // namespace rtrg

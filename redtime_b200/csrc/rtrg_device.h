@@ -31,6 +31,8 @@ enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55 };
 enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
 #endif
 enum { BIL_R = 8 };  // output rows per CTA of the bilinear kernel
+// output groups of one evaluation of the mode-coupling integrals
+enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15 };
 enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
 
 struct IntegralTabs {
@@ -54,6 +56,8 @@ struct IntegralTabs {
   const int *ex_n0;       // [np] first node of the 4-point stencil
   const double *ex_w;     // [np][4]
   const double *ex_dx;    // [np] lnk - lnk[nk-1] for the power-law extrapolation, else 0
+  // beta-side spectra (bit c = P_{cd=c}) of kernel n consumed by output group g = A, R, PT, PMR
+  unsigned char need_cd[4][N_JKERN];
   // assembly table (sorted by output row)
   int n_terms;
   const int *t_start;     // [56]
@@ -91,6 +95,7 @@ struct Batch {
   int *i_out, *flag_out, *flag_step, *flag_acc, *final_step, *done;
   int *m_full_step, *m_full_acc, *m_out_int;  // masks of the integral launches
   long long *counters;     // [B][4]
+  long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
   int *n_active;           // [1]
   // outputs
   double *out;             // concatenated tables

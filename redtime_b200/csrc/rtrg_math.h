@@ -380,12 +380,22 @@ struct GrowthCtx {
   const double *brow;  // beta row pre-reduced at this wavenumber (clamped k)
   long long bstride;   // stride between successive a-nodes of brow
 };
+// One evaluation costs one pow + one exp (the dark-energy factor E, shared by H^2 and
+// dlnH/dlna) and a handful of multiplications: the integer powers of a are products, not
+// pow() calls -- this function runs ~12k times per table entry (13 stages x ~940 attempts).
 RT_HD void growth_rhs(const GrowthCtx &g, double a, const double y[2], double f[2]) {
-  const double F0 = 1.5 * g.bg.Om / (pow(a, 5.0) * bgs_H2(g.bg, a));
-  const double F1 = (3.0 + bgs_dlnH(g.bg, a)) / a;
-  const double beta = (a < 1e-3) ? g.bg.fn : beta_row(g.bt, g.brow, fmin(a, 1.0), g.bstride);
+  const BgStatic &s = g.bg;
+  const double a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a4 * a;
+  const double E = bgs_E(s, a), dEda = 3.0 * E * (s.wa - (1.0 + s.w0 + s.wa) / a);
+  const double Y = bgs_Y(s, a), dYda = bgs_dYda(s, a);
+  const double H2 = (s.Om - s.On) * (1.0 + Y) / a3 + s.OL * E + s.Og / a4;  // hdr:473-476
+  const double dlnH = 0.5 * a / H2 *
+                      (s.fc * s.Om * (-3.0 * (1.0 + Y) + a * dYda) / a4 + s.OL * dEda - 4.0 * s.Og / a5);
+  const double F0 = 1.5 * s.Om / (a5 * H2);
+  const double F1 = (3.0 + dlnH) / a;
+  const double beta = (a < 1e-3) ? s.fn : beta_row(g.bt, g.brow, fmin(a, 1.0), g.bstride);
   f[0] = y[1];
-  f[1] = -F1 * y[1] + F0 * (g.bg.fc + beta) * y[0];  // F_MG = 0 (hdr:151-153)
+  f[1] = -F1 * y[1] + F0 * (s.fc + beta) * y[0];  // F_MG = 0 (hdr:151-153)
 }
 
 struct PDTableau {

@@ -100,3 +100,21 @@ def test_batch_of_identical_and_mixed_cosmologies(example1_dir, example1_full_di
     _, orc = load_oracle("full")
     assert np.all(col_err(tables[1][:, :, :10], orc.reshape(7, NK, 17)[:, :, :10]) < 1e-5)
     h.close()
+
+
+def test_batch_front_end_writes_reference_format(tmp_path, golden_example1):
+    """redtime_b200.batch: run directories in, redTime_<MODEL>.dat out (the file a
+    `redTime > redTime_<MODEL>.dat` run of the reference leaves, scripts/runRedTime:196-229)."""
+    from redtime_b200 import batch
+    from conftest import make_example1_dir
+    d1 = make_example1_dir(str(tmp_path / "M001"))
+    d2 = make_example1_dir(str(tmp_path / "M002"), switches=[1, 0, 1, 1])
+    res = batch.run_batch([d1, d2])
+    assert res == {d1: 0, d2: 0}
+    hdr, arr = parse_tables(open(os.path.join(d1, "redTime_M001.dat")).read())
+    ghdr, gold = golden_example1
+    assert hdr == ghdr
+    assert np.max(np.abs(arr[:, :10] / gold[:, :10] - 1)) < 1e-9
+    _, full = parse_tables(open(os.path.join(d2, "redTime_M002.dat")).read())
+    _, orc = load_oracle("full")
+    assert np.max(np.abs(full[:, :10] / orc[:, :10] - 1)) < 1e-9

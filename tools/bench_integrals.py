@@ -22,7 +22,7 @@ h.set_profiling(True)
 h.bench_integrals(reps)
 p = h.profile()
 g = rt.grid_info(nk)
-flop = 14 * nk * (6.0 * g["nsup"] ** 2 + 18.0 * g["nsup"]) * B * reps
+flop = 42 * nk * (2.0 * g["nsup"] ** 2 + 6.0 * g["nsup"]) * B * reps
 peak = rt.dfma_peak_tflops(0, 0.3)
 n, ms = p["k_bilinear"]
 print("variant=%s B=%d nk=%d: k_bilinear %.3f ms/launch, %.2f TFLOP/s algorithmic = %.1f%% of measured DFMA peak %.2f; "
