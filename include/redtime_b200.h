@@ -148,9 +148,11 @@ const char *rtrg_profile_name(int cat);
 int rtrg_profile_query(const rtrg_handle *h, int cat, long long *n_launches, double *total_ms);
 
 /* Tuning aid: evaluate the mode-coupling integrals of the linear spectra at z1l for every
- * cosmology of the batch `reps` times (all 14 bilinear kernels); read the timings with
- * rtrg_profile_query().  Results go to the scratch source buffer only.                  */
-int rtrg_bench_integrals(rtrg_handle *h, int reps);
+ * cosmology of the batch `reps` times; read the timings with rtrg_profile_query() and the work
+ * with rtrg_matvec_sets().  groups: bit 0 A, 1 R, 2 P_T,jm, 3 P_MR,n, 4 every raw product;
+ * identical != 0 uses the identical-spectra shortcut of the 1-loop cache.  Results go to the
+ * scratch source buffer only.                                                            */
+int rtrg_bench_integrals(rtrg_handle *h, int reps, int groups, int identical);
 /* FP64 FMA pipe peak of `device` in TFLOP/s (register-resident DFMA loop, best launch over
  * about `seconds` of device time): the roofline denominator of the integral kernels.    */
 int rtrg_bench_dfma(int device, double seconds, double *tflops);

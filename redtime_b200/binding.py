@@ -73,7 +73,7 @@ def load_library():
     lib.rtrg_profile_name.restype = C.c_char_p
     lib.rtrg_profile_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _dp]
     lib.rtrg_bench_dfma.argtypes = [C.c_int, C.c_double, _dp]
-    lib.rtrg_bench_integrals.argtypes = [C.c_void_p, C.c_int]
+    lib.rtrg_bench_integrals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.rtrg_kshard_nccl_id.argtypes = [C.c_char_p]
     lib.rtrg_kshard_init_nccl.argtypes = [C.c_void_p, C.c_char_p]
     lib.rtrg_kshard_loopback_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
@@ -324,8 +324,8 @@ class RedTimeB200:
     def kshard_init_loopback(self, group):
         _check(self.lib.rtrg_kshard_init_loopback(self.h, group.g))
 
-    def bench_integrals(self, reps=1):
-        _check(self.lib.rtrg_bench_integrals(self.h, int(reps)))
+    def bench_integrals(self, reps=1, groups=31, identical=0):
+        _check(self.lib.rtrg_bench_integrals(self.h, int(reps), int(groups), int(identical)))
 
     def set_profiling(self, on=True):
         _check(self.lib.rtrg_set_profiling(self.h, int(on)))

@@ -899,13 +899,13 @@ int rtrg_kshard_init_loopback(rtrg_handle *h, rtrg_loopback *g) {
 }
 void rtrg_kshard_loopback_free(rtrg_loopback *g) { delete g; }
 
-int rtrg_bench_integrals(rtrg_handle *h, int reps) {
+int rtrg_bench_integrals(rtrg_handle *h, int reps, int groups, int identical) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   if (!h->prepared) return fail(RTRG_EINVAL, "rtrg_prepare() has not been called");
   CU(cudaSetDevice(h->cfg.device));
   const int nk = h->S.nk;
   for (int r = 0; r < reps; r++)
-    h->launches += launch_integrals(h->tb, h->S, h->S.y_z1l, 3LL * nk, h->S.src, nullptr, nullptr, GRP_ALL, 0,
+    h->launches += launch_integrals(h->tb, h->S, h->S.y_z1l, 3LL * nk, h->S.src, nullptr, nullptr, groups, identical,
                                     h->stream, h->prof);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
@@ -986,7 +986,7 @@ static int run_integrals_hook(rtrg_handle *h, int icosmo, const double *lnP3nk, 
   double *yslot = h->S.ytmp + (size_t)icosmo * N_U * nk;
   CU(cudaMemcpyAsync(yslot, lnP3nk, 3 * nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->launches += launch_integrals(h->tb, h->S, h->S.ytmp, (long long)N_U * nk, h->S.src, want_raw ? h->d_raw : nullptr,
-                                  h->d_hookmask, GRP_ALL, 0, h->stream, nullptr);
+                                  h->d_hookmask, GRP_ALL | GRP_RAW, 0, h->stream, nullptr);
   return RTRG_OK;
 }
 

@@ -404,6 +404,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     int need = 0;
     for (int gi = 0; gi < 4; gi++)
       if (groups & (1 << gi)) need |= tb.need_cd[gi][n];
+    if (groups & GRP_RAW) need = 7;  // parity hooks: every product, used by an output or not
     if (!need) continue;
     if (identical) need = 1;
     BilItem it;

@@ -32,7 +32,7 @@ enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
 #endif
 enum { BIL_R = 8 };  // output rows per CTA of the bilinear kernel
 // output groups of one evaluation of the mode-coupling integrals
-enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15 };
+enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15, GRP_RAW = 16 };
 enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
 
 struct IntegralTabs {

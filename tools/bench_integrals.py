@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Micro-benchmark of the integral kernels: B cosmologies, `reps` full evaluations.
-usage: bench_integrals.py [B] [reps] [nk]   (kernel variant via RTRG_BIL_VARIANT)"""
+"""Micro-benchmark of the integral kernels: B cosmologies, `reps` evaluations per output-group
+mix.  usage: bench_integrals.py [B] [reps] [nk]   (kernel variant via RTRG_BIL_VARIANT)"""
 import os
 import sys
 
@@ -14,17 +14,37 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 nk = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 base = wl.load_example1(16)
 h = rt.RedTimeB200(nk=nk)
-for c in wl.make_cosmologies(B, base):
-    h.add_cosmology(c)
+h.add_cosmologies(wl.make_cosmologies(B, base))
 h.prepare()
-h.bench_integrals(2)
-h.set_profiling(True)
-h.bench_integrals(reps)
-p = h.profile()
 g = rt.grid_info(nk)
-flop = 42 * nk * (2.0 * g["nsup"] ** 2 + 6.0 * g["nsup"]) * B * reps
 peak = rt.dfma_peak_tflops(0, 0.3)
-n, ms = p["k_bilinear"]
-print("variant=%s B=%d nk=%d: k_bilinear %.3f ms/launch, %.2f TFLOP/s algorithmic = %.1f%% of measured DFMA peak %.2f; "
-      "others: %s" % (os.environ.get("RTRG_BIL_VARIANT", "0"), B, nk, ms / n, flop / ms * 1e-9, 100 * flop / ms * 1e-9 / peak, peak,
-                      {k: round(v[1] / max(v[0], 1), 3) for k, v in p.items() if v[0] and k != "k_bilinear"}))
+flop_set = nk * (2.0 * g["nsup"] ** 2 + 6.0 * g["nsup"])
+print("variant=%s B=%d nk=%d  measured DFMA peak %.2f TFLOP/s" % (os.environ.get("RTRG_BIL_VARIANT", "0"), B, nk, peak))
+row, src, idx, kpw, cf = rt.assembly_terms()
+
+
+def sets(groups, ident):
+    need = {}
+    for r, s_, i in zip(row, src, idx):
+        if s_ not in (0, 2):
+            continue
+        gi = 0 if r < 14 else 1 if r < 38 else 2 if r < 47 else 3
+        if groups & (1 << gi):
+            n = i // 9 + (7 if s_ == 2 else 0)
+            need[n] = need.get(n, 0) | (1 << (i % 3))
+    if groups & 16:
+        need = {n: 7 for n in range(14)}
+    return sum(1 if ident else bin(v).count("1") for v in need.values())
+
+
+for name, groups, ident in (("every product", 31, 0), ("RHS: A+R", 3, 0), ("output: P_T,jm", 4, 0),
+                            ("z1l cache: A+R, identical spectra", 3, 1)):
+    h.bench_integrals(1, groups, ident)
+    h.set_profiling(True)
+    h.bench_integrals(reps, groups, ident)
+    p = h.profile()
+    h.set_profiling(False)
+    n, ms = p["k_bilinear"]
+    ns = sets(groups, ident)
+    tf = flop_set * ns * B * reps / ms * 1e-9
+    print("  %-36s %2d sets  k_bilinear %8.3f ms/eval  %6.2f TFLOP/s = %4.1f%% of peak" % (name, ns, ms / reps, tf, 100 * tf / peak))
