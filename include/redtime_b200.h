@@ -113,6 +113,12 @@ int rtrg_device_init(rtrg_handle *h);
  * out / hdr / hdr0 may be NULL: the tables then stay on the device (no D2H copy).     */
 int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *hdr0,
              int *status);
+/* Zero-copy read-back after rtrg_run(h, NULL, 0, NULL, NULL, status): one device->host copy
+ * into page-locked buffers owned by the handle.  The returned pointers (layouts as in rtrg_run)
+ * stay valid until the next rtrg_prepare / rtrg_fetch_outputs / rtrg_destroy on this handle. */
+int rtrg_fetch_outputs(rtrg_handle *h, const double **out, size_t *out_len, const double **hdr,
+                       const double **hdr0);
+
 /* ---- one high-resolution cosmology sharded over its k-rows ---------------
  * Create one handle per rank with cfg.k_shards = number of ranks and cfg.k_rank = this rank
  * (nk/8 must be divisible by k_shards), add the SAME cosmologies to each, attach a transport,

@@ -81,6 +81,8 @@ def load_library():
     lib.rtrg_kshard_loopback_free.argtypes = [C.c_void_p]
     lib.rtrg_kshard_loopback_free.restype = None
     lib.rtrg_run.argtypes = [C.c_void_p, _dp, C.c_size_t, _dp, _dp, _ip]
+    lib.rtrg_fetch_outputs.argtypes = [C.c_void_p, C.POINTER(_dp), C.POINTER(C.c_size_t), C.POINTER(_dp),
+                                       C.POINTER(_dp)]
     lib.rtrg_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     lib.rtrg_extrap_P.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.rtrg_integrals_full.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
@@ -338,6 +340,26 @@ class RedTimeB200:
             self.lib.rtrg_profile_query(self.h, cat, C.byref(n), C.byref(ms))
             out[self.lib.rtrg_profile_name(cat).decode()] = (int(n.value), float(ms.value))
         return out
+
+    def run_pinned(self, raise_on_ode_failure=True):
+        """Like run(), but the returned arrays are views of page-locked buffers owned by the
+        handle (no pageable copy); they are valid until the next prepare()/run_pinned()."""
+        B = self.n_cosmo
+        status = np.zeros(B, np.int32)
+        rc = self.lib.rtrg_run(self.h, None, 0, None, None, status.ctypes.data_as(_ip))
+        if rc != 0 and (rc != -5 or raise_on_ode_failure):
+            _check(rc)
+        po, ph, ph0, n = _dp(), _dp(), _dp(), C.c_size_t()
+        _check(self.lib.rtrg_fetch_outputs(self.h, C.byref(po), C.byref(n), C.byref(ph), C.byref(ph0)))
+        out = np.ctypeslib.as_array(po, shape=(n.value,))
+        hdr = np.ctypeslib.as_array(ph, shape=(B, MAX_OUT, 5))
+        hdr0 = np.ctypeslib.as_array(ph0, shape=(B, 2))
+        tables, o = [], 0
+        for i in range(B):
+            sz = self._nout[i] * self.nk * self.num_columns(i)
+            tables.append(out[o:o + sz].reshape(self._nout[i], self.nk, -1))
+            o += sz
+        return tables, hdr, hdr0, status
 
     def run(self, raise_on_ode_failure=True):
         """Returns (tables, hdr, hdr0, status): tables[i] has shape [n_out_i, nk, ncols_i]."""

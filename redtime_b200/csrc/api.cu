@@ -123,6 +123,12 @@ struct rtrg_handle {
   DeviceArena work;
   double *d_in = nullptr;     // device input pool (mirror of stage)
   size_t d_in_cap = 0, d_in_uploaded = 0;
+  bool d_in_transformed = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done = nullptr;
+  // pinned host mirror of the outputs (rtrg_fetch_outputs)
+  double *h_out = nullptr;
+  size_t h_out_cap = 0;
   double *d_T0 = nullptr;
   double *d_kgrid = nullptr;
   std::vector<double> kgrid;
@@ -259,6 +265,8 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   std::memset(&h->S, 0, sizeof h->S);
   std::memset(&h->tb, 0, sizeof h->tb);
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
   h->stream = h->own_stream;
   if (linear_upload_constants() != 0) {
     delete h;
@@ -366,8 +374,18 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
       w[n + 1 - n0] = t;
     }
   }
-  // --- assembly table sorted by output row
+  // --- assembly table sorted by output row.  Kernels with alpha = beta are symmetric,
+  // T_n[u][v] = T_n[v][u], so J_n(ab,cd) = J_n(cd,ab): terms are redirected to the pair with
+  // ab <= cd, which lets k_bilinear skip beta-side spectra that only the mirrored pairs used
+  // (e.g. the four (2,2,l) Jn0 kernels of P_T,jm need P_11 alone instead of P_01 and P_11).
   std::vector<AsmTerm> terms = assembly_terms();
+  for (AsmTerm &t : terms) {
+    if (t.src != 0 && t.src != 2) continue;
+    const KernSpec ks = kern_spec(t.index / 9 + (t.src == 2 ? 7 : 0));
+    if (ks.alpha != ks.beta) continue;
+    const int ab = (t.index % 9) / 3, cd = t.index % 3;
+    if (ab > cd) t.index = (short)(9 * (t.index / 9) + 3 * cd + ab);
+  }
   std::stable_sort(terms.begin(), terms.end(), [](const AsmTerm &a, const AsmTerm &b) { return a.row < b.row; });
   std::vector<int> t_start(N_SRC + 1, 0);
   std::vector<short> t_src, t_index, t_kpow;
@@ -424,6 +442,9 @@ int rtrg_destroy(rtrg_handle *h) {
   if (h->work.base) cudaFree(h->work.base);
   if (h->d_in) cudaFree(h->d_in);
   h->stage.release();
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->copy_done) cudaEventDestroy(h->copy_done);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RTRG_OK;
@@ -438,8 +459,10 @@ int rtrg_set_stream(rtrg_handle *h, void *cuda_stream) {
 int rtrg_clear_cosmologies(rtrg_handle *h) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   h->cos.clear();
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   h->stage.used = 0;
   h->d_in_uploaded = 0;
+  h->d_in_transformed = false;
   h->prepared = h->uploaded = false;
   return RTRG_OK;
 }
@@ -462,7 +485,7 @@ static int check_cosmology(const rtrg_cosmology *in) {
 }
 static size_t cosmology_doubles(const rtrg_cosmology *in) {
   const size_t nz = in->n_z > 0 ? in->n_z : 0, nkb = in->n_z > 0 ? in->n_kb : 0;
-  return 3 * (size_t)in->n_T + nz + nkb + 2 * nz * nkb;
+  return 3 * (size_t)in->n_T + nz + nkb + nz * nkb;
 }
 // scalars + offsets of one cosmology whose tables start at arena offset `off`
 static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off) {
@@ -485,11 +508,10 @@ static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off) {
   c.offTb = (long long)(off + 2 * nT);
   c.offA = (long long)(off + 3 * nT);
   c.offKb = (long long)(off + 3 * nT + nz);
-  c.offTc = (long long)(off + 3 * nT + nz + nkb);
-  c.offB = (long long)(off + 3 * nT + nz + nkb + nz * nkb);
+  c.offB = (long long)(off + 3 * nT + nz + nkb);
   return hc;
 }
-// copy the caller's tables into the staging arena (raw; the device transforms them)
+// copy the caller's tables into the staging arena (the z=0 columns raw, beta formed here)
 static void stage_cosmology(const rtrg_cosmology *in, const Cosmo &c, double *base) {
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
   std::memcpy(base + c.offT, in->k_T, nT * sizeof(double));
@@ -498,8 +520,12 @@ static void stage_cosmology(const rtrg_cosmology *in, const Cosmo &c, double *ba
   for (size_t i = 0; i < nz; i++) base[c.offA + i] = 1.0 / (1.0 + in->z_interp[i]);
   if (nz) {
     std::memcpy(base + c.offKb, in->k_b, nkb * sizeof(double));
-    std::memcpy(base + c.offTc, in->Tc_b, nz * nkb * sizeof(double));
-    std::memcpy(base + c.offB, in->Tnu_b, nz * nkb * sizeof(double));
+    // beta = f_nu T_nu / T_c (hdr:556-623), formed on the fly: halves the bytes that cross PCIe
+    const double fn = c.On / c.Om;
+    const double *tn = in->Tnu_b, *tc = in->Tc_b;
+    double *dst = base + c.offB;
+    const size_t n = nz * nkb;
+    for (size_t i = 0; i < n; i++) dst[i] = fn * tn[i] / tc[i];
   }
 }
 
@@ -512,6 +538,7 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     need += cosmology_doubles(list[i]);
   }
   CU(cudaSetDevice(h->cfg.device));
+  if (need > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
   if (h->stage.reserve(need) != RTRG_OK) return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", need * sizeof(double));
   const size_t first = h->cos.size();
   size_t off = h->stage.used;
@@ -520,19 +547,42 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     off += cosmology_doubles(list[i]);
   }
   h->stage.used = off;
+  // device pool large enough? then each staged chunk is sent right away on the copy stream,
+  // overlapping the PCIe transfer with the staging of the next chunk
+  if (h->stage.used > h->d_in_cap) {
+    CU(cudaStreamSynchronize(h->copy_stream));
+    double *q = nullptr;
+    const size_t ncap = h->stage.used + h->stage.used / 8;
+    cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
+    if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
+    if (h->d_in) cudaFree(h->d_in);
+    h->d_in = q;
+    h->d_in_cap = ncap;
+    h->d_in_uploaded = 0;  // the staged prefix goes out again with the first chunk
+  }
   // parallel staging: the copies are memory-bound, one thread saturates only ~10 GB/s
   int nth = (int)std::thread::hardware_concurrency();
   nth = std::max(1, std::min(std::min(nth, 16), n));
   double *base = h->stage.base;
-  if (nth == 1) {
-    for (int i = 0; i < n; i++) stage_cosmology(list[i], h->cos[first + i].c, base);
-  } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nth; t++)
-      th.emplace_back([=]() {
-        for (int i = t; i < n; i += nth) stage_cosmology(list[i], h->cos[first + i].c, base);
-      });
-    for (auto &t : th) t.join();
+  const int chunk = std::max(nth, 64);
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int c1 = std::min(n, c0 + chunk);
+    if (nth == 1) {
+      for (int i = c0; i < c1; i++) stage_cosmology(list[i], h->cos[first + i].c, base);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nth; t++)
+        th.emplace_back([=]() {
+          for (int i = c0 + t; i < c1; i += nth) stage_cosmology(list[i], h->cos[first + i].c, base);
+        });
+      for (auto &t : th) t.join();
+    }
+    const size_t upto = (c1 == n) ? h->stage.used : (size_t)h->cos[first + c1].c.offT;
+    if (upto > h->d_in_uploaded) {
+      CU(cudaMemcpyAsync(h->d_in + h->d_in_uploaded, base + h->d_in_uploaded,
+                         (upto - h->d_in_uploaded) * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      h->d_in_uploaded = upto;
+    }
   }
   h->prepared = h->uploaded = false;
   return RTRG_OK;
@@ -684,21 +734,15 @@ int rtrg_prepare(rtrg_handle *h) {
   cudaStream_t st = h->stream;
   // zero everything once (the Prev padding, the Q/I state rows ... rely on it)
   CU(cudaMemsetAsync(h->work.base, 0, h->work.used, st));
-  // --- input pool: send the not yet uploaded tail of the staging arena
-  if (h->stage.used > h->d_in_cap) {
-    double *q = nullptr;
-    const size_t ncap = h->stage.used + h->stage.used / 8;
-    cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
-    if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
-    if (h->d_in) cudaFree(h->d_in);
-    h->d_in = q;
-    h->d_in_cap = ncap;
-    h->d_in_uploaded = 0;
+  // --- input pool: rtrg_add_cosmologies already sent the staged tables on the copy stream.  A
+  // repeated rtrg_prepare (the log transform below consumed the raw columns) sends them again.
+  if (h->d_in_transformed) {
+    CU(cudaMemcpyAsync(h->d_in, h->stage.base, h->stage.used * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    h->d_in_uploaded = h->stage.used;
   }
-  // (the in-place transform below consumes the raw columns, so a re-prepare re-sends all)
-  h->d_in_uploaded = 0;
-  CU(cudaMemcpyAsync(h->d_in, h->stage.base, h->stage.used * sizeof(double), cudaMemcpyHostToDevice, st));
-  h->d_in_uploaded = h->stage.used;
+  CU(cudaEventRecord(h->copy_done, h->copy_stream));
+  CU(cudaStreamWaitEvent(st, h->copy_done, 0));
+  h->d_in_transformed = true;
   S.in = h->d_in;
   CU(cudaMemcpyAsync(S.cosmo, cs.data(), B * sizeof(Cosmo), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.zout, zout.data(), zout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -854,6 +898,35 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   }
   if (n_active > 0) return fail(RTRG_EODE, "integration did not finish within %lld rounds", max_rounds);
   if (worst) return fail(worst, "at least one cosmology failed (see status[])");
+  return RTRG_OK;
+}
+
+int rtrg_fetch_outputs(rtrg_handle *h, const double **out, size_t *out_len, const double **hdr, const double **hdr0) {
+  if (!h) return fail(RTRG_EINVAL, "null handle");
+  if (!h->prepared) return fail(RTRG_EINVAL, "rtrg_prepare() has not been called");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t B = h->S.B, n_hdr = B * MAX_OUT * 5, n_hdr0 = B * 2, need = h->out_total + n_hdr + n_hdr0;
+  if (need > h->h_out_cap) {
+    if (h->h_out) cudaFreeHost(h->h_out);
+    h->h_out = nullptr;
+    h->h_out_cap = 0;
+    const size_t ncap = need + need / 8;
+    if (cudaHostAlloc((void **)&h->h_out, ncap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RTRG_ENOMEM, "pinned output buffer of %zu bytes", ncap * sizeof(double));
+    }
+    h->h_out_cap = ncap;
+  }
+  cudaStream_t st = h->stream;
+  double *p_out = h->h_out, *p_hdr = p_out + h->out_total, *p_hdr0 = p_hdr + n_hdr;
+  CU(cudaMemcpyAsync(p_out, h->S.out, h->out_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(p_hdr, h->S.hdr, n_hdr * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(p_hdr0, h->S.hdr0, n_hdr0 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out) *out = p_out;
+  if (out_len) *out_len = h->out_total;
+  if (hdr) *hdr = p_hdr;
+  if (hdr0) *hdr0 = p_hdr0;
   return RTRG_OK;
 }
 

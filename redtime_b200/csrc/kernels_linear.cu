@@ -35,9 +35,8 @@ __device__ __forceinline__ double slot_k(const Batch &S, const double *kgrid, in
   return kk < S.nk ? kgrid[kk] : exp(S.lnkg[kk - S.nk]);
 }
 
-// In-place transform of the raw CAMB columns (once per upload):
+// In-place transform of the raw z=0 transfer columns (once per upload):
 //   k_T -> ln k;  Tc_T -> ln(T_cb / T_cb[0]) with T_cb = f_b T_b + f_c T_c  (hdr:804-823)
-//   Tnu_b -> beta = f_nu T_nu / T_c                                          (hdr:556-623)
 __global__ void k_prep_T0(Batch S, double *__restrict__ T0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= S.B) return;
@@ -48,17 +47,11 @@ __global__ void k_prep_T0(Batch S, double *__restrict__ T0) {
 __global__ void k_prep_inputs(Batch S, const double *__restrict__ T0) {
   const int b = blockIdx.y;
   const Cosmo &c = S.cosmo[b];
-  const double f_b = c.Ob / (c.Om - c.On), f_c = 1.0 - f_b, fn = c.On / c.Om, t0 = T0[b];
-  const long long nB = (long long)c.n_z * c.n_kb, n = c.nT + nB;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (i < c.nT) {
-      const double Ti = f_b * S.in[c.offTb + i] + f_c * S.in[c.offLT + i];
-      S.in[c.offT + i] = log(S.in[c.offT + i]);
-      S.in[c.offLT + i] = log(Ti / t0);
-    } else {
-      const long long j = i - c.nT;
-      S.in[c.offB + j] = fn * S.in[c.offB + j] / S.in[c.offTc + j];
-    }
+  const double f_b = c.Ob / (c.Om - c.On), f_c = 1.0 - f_b, t0 = T0[b];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.nT; i += gridDim.x * blockDim.x) {
+    const double Ti = f_b * S.in[c.offTb + i] + f_c * S.in[c.offLT + i];
+    S.in[c.offT + i] = log(S.in[c.offT + i]);
+    S.in[c.offLT + i] = log(Ti / t0);
   }
 }
 int launch_prep_inputs(const Batch &S, double *T0, int max_rows, cudaStream_t st, Profiler *prof) {

@@ -33,8 +33,8 @@ struct Cosmo {
   int sw_nl, sw_1l, sw_pl, sw_pr;
   int n_out;
   // tables (offsets into the pooled device arrays, in doubles)
-  // tables: offsets (in doubles) into the single device-resident input pool.  The pool is
-  // uploaded raw (columns of the CAMB files) and transformed in place by k_prep_inputs.
+  // tables: offsets (in doubles) into the single device-resident input pool.  The transfer
+  // columns are uploaded raw and turned into log tables in place by k_prep_inputs.
   int nT;             // rows of the z=0 transfer table
   long long offT;     // k_T       -> ln k            (hdr:812-823)
   long long offLT;    // Tc_T      -> ln(T_cb/T_cb[0])
@@ -42,8 +42,7 @@ struct Cosmo {
   int n_z, n_kb;      // beta table a-nodes x k-nodes
   long long offA;     // a nodes = 1/(1+z_interp)
   long long offKb;    // k nodes of the interpolation files
-  long long offTc;    // Tc_b [n_z][n_kb] (raw, consumed by the transform)
-  long long offB;     // Tnu_b [n_z][n_kb] -> beta = f_nu T_nu / T_c  (hdr:556-623)
+  long long offB;     // beta = f_nu T_nu / T_c [n_z][n_kb]  (hdr:556-623; formed while staging)
   // results of the device-side initialisation
   double Norm;        // sigma_8 normalisation (hdr:874)
   double sigv2_0;     // sigma_v^2(z=0)       (hdr:961)

@@ -31,7 +31,10 @@ def sets(groups, ident):
         gi = 0 if r < 14 else 1 if r < 38 else 2 if r < 47 else 3
         if groups & (1 << gi):
             n = i // 9 + (7 if s_ == 2 else 0)
-            need[n] = need.get(n, 0) | (1 << (i % 3))
+            ab, cd = (i % 9) // 3, i % 3
+            if n in (0, 3, 6, 10, 11, 12, 13):  # symmetric kernels: pair (ab,cd) served by (min,max)
+                cd = max(ab, cd)
+            need[n] = need.get(n, 0) | (1 << cd)
     if groups & 16:
         need = {n: 7 for n in range(14)}
     return sum(1 if ident else bin(v).count("1") for v in need.values())
