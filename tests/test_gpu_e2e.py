@@ -118,3 +118,19 @@ def test_batch_front_end_writes_reference_format(tmp_path, golden_example1):
     _, full = parse_tables(open(os.path.join(d2, "redTime_M002.dat")).read())
     _, orc = load_oracle("full")
     assert np.max(np.abs(full[:, :10] / orc[:, :10] - 1)) < 1e-9
+
+
+def test_pinned_read_back_equals_copying_run(example1_dir):
+    h = rt.RedTimeB200()
+    h.add_cosmologies([rt.read_run_dir(example1_dir)] * 3)
+    h.prepare()
+    t1, hdr1, hdr01, st1 = h.run()
+    t2, hdr2, hdr02, st2 = h.run_pinned()
+    for a, b in zip(t1, t2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(hdr1, hdr2) and np.array_equal(hdr01, hdr02)
+    # a second prepare() re-sends the staged tables (the log transform consumed them)
+    h.prepare()
+    t3, *_ = h.run()
+    assert np.array_equal(t3[1], t1[1])
+    h.close()
