@@ -312,16 +312,51 @@ def run_b200(a, rank, world, local_rank):
         for _ in range(steps):
             tables, hdr, hdr0, status = e2e_step()
         torch.cuda.synchronize()
-        t_e2e = reduce_max(time.perf_counter() - t0)
+        t_serial = reduce_max(time.perf_counter() - t0)
         h2d = sum(c["k_T"].nbytes * 3 + c["k_b"].nbytes + c["Tc_b"].nbytes + c["z_interp"].nbytes for c in cosmos)
         h2d += B * (400 + 64 * 8 * 3)  # per-cosmology scalars and output redshift lists
         d2h = sum(t.nbytes for t in tables) + hdr.nbytes + hdr0.nbytes
-        e2e = {"value": world * outputs_per_step * steps / t_e2e, "unit": UNIT,
+        checksum = float(sum(float(t[-1, :, 7].sum()) for t in tables))
+
+        # double-buffered: a second handle stages and uploads batch i+1 (host threads + copy
+        # engine) while batch i is computed and read back -- every step still moves its own
+        # inputs host->device and its own tables device->host inside the timed region
+        h2 = rt.RedTimeB200(device=local_rank, nk=NK)
+        hs = [h, h2]
+        for hh in hs:                      # warm both handles' arenas
+            hh.clear()
+            hh.add_cosmologies(cosmos)
+            hh.prepare()
+            hh.run_pinned()
+        sync_all()
+        t0 = time.perf_counter()
+        pending = threading.Thread(target=lambda: (hs[0].clear(), hs[0].add_cosmologies(cosmos)))
+        pending.start()
+        sums = []
+        for i in range(steps):
+            pending.join()
+            cur = hs[i % 2]
+            if i + 1 < steps:
+                nxt = hs[(i + 1) % 2]
+                pending = threading.Thread(target=lambda nxt=nxt: (nxt.clear(), nxt.add_cosmologies(cosmos)))
+                pending.start()
+            cur.prepare()
+            tb_, _, _, st_ = cur.run_pinned()
+            sums.append(float(sum(float(t[-1, :, 7].sum()) for t in tb_)))
+        torch.cuda.synchronize()
+        t_pipe = reduce_max(time.perf_counter() - t0)
+        h2.close()
+        assert all(abs(x - checksum) <= 1e-12 * abs(checksum) for x in sums), "pipelined results differ"
+        e2e = {"value": world * outputs_per_step * steps / t_pipe, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * t_e2e / steps, "timing": "wall clock around the C-ABI calls, max over ranks",
-               "path": "rtrg_add_cosmologies (caller's pageable numpy buffers -> page-locked staging on 16 host "
-                       "threads, chunked H2D overlapped) -> rtrg_prepare -> rtrg_run -> rtrg_fetch_outputs (D2H "
-                       "into page-locked memory)"}
+               "ms_per_step": 1e3 * t_pipe / steps,
+               "serial_value": world * outputs_per_step * steps / t_serial, "serial_ms_per_step": 1e3 * t_serial / steps,
+               "timing": "wall clock around the C-ABI calls, max over ranks",
+               "path": "per step: rtrg_add_cosmologies (caller's pageable numpy buffers -> page-locked staging on "
+                       "host threads, chunked H2D on a copy stream) -> rtrg_prepare -> rtrg_run -> "
+                       "rtrg_fetch_outputs (D2H into page-locked memory).  value: double-buffered over two "
+                       "handles (batch i+1 is staged/uploaded while batch i computes); serial_value: one handle, "
+                       "nothing overlapped"}
 
     if rank != 0:
         return
