@@ -120,7 +120,7 @@ def run_reference_arm(a, rank):
     warm = a.warmup if a.warmup is not None else 1
     binary = reference_binary()
     if binary is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/redTime not built (make -C oracle)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/redTime not built (make -C oracle)"}))
         return
     nproc = a.ref_procs or host_cores()
     with tempfile.TemporaryDirectory() as tmp:
@@ -139,7 +139,7 @@ def run_reference_arm(a, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def REDSHIFTS():
@@ -386,7 +386,7 @@ def run_b200(a, rank, world, local_rank):
                        % (sum(c["Tc_b"].nbytes * 2 for c in cosmos) / 1e9)},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernel_ms_in_timed_region": kernels}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -502,7 +502,27 @@ def run_kshard(a, rank, world, local_rank):
             "counters": cnt,
             "parity_max_rel_err_cols_1_10_vs_oracle": None if err is None else float(err[:10].max()),
             "kernel_ms_in_timed_region": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in prof.items() if v[0]}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """NCCL and torchrun print banners on stdout; keep fd 1 for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -518,6 +538,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29517"] + sys.argv
         sys.exit(subprocess.call(cmd))
+    quiet_stdout()
     if a.workload == "kshard":
         run_kshard(a, rank, world, local_rank)
     else:
