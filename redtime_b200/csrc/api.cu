@@ -700,6 +700,8 @@ int rtrg_prepare(rtrg_handle *h) {
     S.m_out_int = A.take<int>(B);
     S.counters = A.take<long long>((size_t)4 * B);
     S.matvecs = A.take<long long>(B);
+    S.act = A.take<int>(B);
+    S.nact = A.take<int>(1);
     S.n_active = A.take<int>(1);
     S.out = A.take<double>(h->out_total);
     S.hdr = A.take<double>((size_t)B * MAX_OUT * 5);

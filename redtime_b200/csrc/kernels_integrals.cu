@@ -246,6 +246,145 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
+// ---------------------------------------------------------------------------- k_bilinear_packed
+// Batch variant: a CTA always carries THREE (cosmology, beta-side spectrum) slots through the
+// same T stream, taken from consecutive entries of the list {active cosmologies} x {spectra of
+// the item}, so every T element feeds 8 rows x 3 slots = 24 DFMAs whatever the number of spectra
+// the item needs (1 for the 1-loop cache, 2 for most P_T,jm kernels, 3 inside the RHS).
+// act[0..*nact) lists the unmasked cosmologies in ascending order (k_compact).
+__global__ void k_compact(const int *__restrict__ mask, int B, int *__restrict__ act, int *__restrict__ nact) {
+  const int lane = threadIdx.x;
+  int off = 0;
+  for (int base = 0; base < B; base += 32) {
+    const int b = base + lane;
+    const int m = (b < B) && (!mask || mask[b]);
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (m) act[off + __popc(bal & ((1u << lane) - 1u))] = b;
+    off += __popc(bal);
+  }
+  if (lane == 0) *nact = off;
+}
+
+template <int R, int TPB, int VC>
+__global__ void __launch_bounds__(TPB, 2)
+    k_bilinear_packed(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+                      double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int ncd, int row0,
+                      const int *__restrict__ act, const int *__restrict__ nact) {
+  constexpr int NS = 3;
+  const BilItem item = L.it[blockIdx.y];
+  const int n = item.n;
+  const int nslots = (*nact) * ncd;
+  const int slot0 = NS * blockIdx.z;
+  if (slot0 >= nslots) return;
+  const int rb = blockIdx.x / tb.nchunk, chunk = blockIdx.x - rb * tb.nchunk;
+  extern __shared__ __align__(128) double sm[];
+  double *s_a = sm;                     // [NS][3][LP]: the three spectra of each slot's cosmology
+  double *s_red = sm + NS * 3 * tb.LP;  // [TPB/32][9R]
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int LP = tb.LP, ldT = tb.ldT;
+  const uint32_t bytes = 3u * (uint32_t)LP * 8u;
+
+  int e_q[NS], cd_q[NS];
+  bool ok_q[NS];
+#pragma unroll
+  for (int q = 0; q < NS; q++) {
+    const int sl = min(slot0 + q, nslots - 1);
+    ok_q[q] = (slot0 + q) < nslots;
+    e_q[q] = act[sl / ncd];
+    cd_q[q] = item.cd[sl - (sl / ncd) * ncd];
+  }
+
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&mbar, NS * bytes);
+#pragma unroll
+    for (int q = 0; q < NS; q++) tma_bulk_g2s(s_a + q * 3 * LP, Prev + (long long)e_q[q] * 3 * LP, bytes, &mbar);
+  }
+
+  const int i0 = row0 + rb * R;
+  const int tu = chunk * TPB + tid;
+  const bool active = tu < tb.NV;
+  const int tuc = active ? tu : tb.NV - 1;
+  const double *Tp = tb.Tc + ((size_t)n * tb.NUp + i0) * ldT + i0 + tuc;
+  const double *s_c[NS];
+#pragma unroll
+  for (int q = 0; q < NS; q++) s_c[q] = s_a + (q * 3 + cd_q[q]) * LP;
+
+  double acc[R][NS];
+#pragma unroll
+  for (int r = 0; r < R; r++)
+#pragma unroll
+    for (int q = 0; q < NS; q++) acc[r][q] = 0.0;
+  double tcur[VC], tnxt[VC];
+#pragma unroll
+  for (int s = 0; s < VC; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
+
+  mbar_wait(&mbar, 0);
+
+  const int NVp = tb.NVp;
+  constexpr int NW = (VC + R) / 2;
+  for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
+    if (tv0 + VC < NVp) {
+      const double *Tn = Tp + (size_t)(tv0 + VC) * ldT;
+#pragma unroll
+      for (int s = 0; s < VC; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; q++) {
+      double w[2 * NW];
+      const double2 *wp = reinterpret_cast<const double2 *>(s_c[q] + tv0);
+#pragma unroll
+      for (int i = 0; i < NW; i++) {
+        const double2 v = wp[i];
+        w[2 * i] = v.x;
+        w[2 * i + 1] = v.y;
+      }
+#pragma unroll
+      for (int s = 0; s < VC; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r][q] = fma(tcur[s], w[s - r + R - 1], acc[r][q]);
+    }
+#pragma unroll
+    for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
+  }
+
+  // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r] * S_u[r]; s_red slot = q*3 + ab
+  static_assert(R == 8, "the epilogue reduction is written for 8 rows per CTA");
+  const int nab = L.replicate ? 1 : 3;
+#pragma unroll
+  for (int q = 0; q < NS; q++) {
+    for (int ab = 0; ab < nab; ab++) {
+      double prod[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const double m = active ? s_a[(q * 3 + ab) * LP + (R - 1) + tu - r] : 0.0;
+        prod[r] = m * acc[r][q];
+      }
+      warp_sum_multi<R>(prod, lane);
+      if ((lane & 3) == 0) s_red[warp * (9 * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
+    }
+  }
+  __syncthreads();
+  if (tid < 9 * R) {
+    const int slot = tid / R, r = tid - slot * R, q = slot / 3, ab = slot - 3 * q;
+    // Jn0 only feeds the RSD terms (rt:804): cosmologies without them keep their old entries
+    if (ok_q[q] && ab < nab && !(n >= 7 && !cosmo[e_q[q]].sw_pr)) {
+      double s = 0.0;
+#pragma unroll 1
+      for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
+      double *dst = Jpart + (((long long)e_q[q] * N_JKERN + n) * tb.nchunk + chunk) * 9 * tb.nk + i0 + r;
+      if (L.replicate) {
+#pragma unroll
+        for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
+      } else {
+        dst[(long long)(ab * 3 + cd_q[q]) * tb.nk] = s;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- k_jlo
 // J_{000}(P00,P00) at the padded row nloMR, needed by P_MR,4..6 (rt:1252,1267-1272)
 __global__ void __launch_bounds__(256)
@@ -368,7 +507,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------- launchers
-enum { BIL_TPB = 352 };
+enum { BIL_TPB = 352, BIL_PACK_MIN_B = 6 };  // batches of >= 6 cosmologies use the packed kernel
 // kernel variant (tuning knob, RTRG_BIL_VARIANT): 0 = 2 CTAs/SM (default); 1 = 1 CTA/SM
 static int g_bil_variant = 0;
 
@@ -425,11 +564,26 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     launches++;
   }
   RT_TIC(prof, PC_BILINEAR, st);
-  launch_bilinear_class<1>(tb, S, L[0], nit[0], row0, nrows, mask, st);
-  launch_bilinear_class<2>(tb, S, L[1], nit[1], row0, nrows, mask, st);
-  launch_bilinear_class<3>(tb, S, L[2], nit[2], row0, nrows, mask, st);
+  if (B >= BIL_PACK_MIN_B && g_bil_variant != 1) {
+    // batch: three (cosmology, spectrum) slots per CTA
+    k_compact<<<1, 32, 0, st>>>(mask, B, S.act, S.nact);
+    launches++;
+    const size_t smem = (size_t)(9 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
+    for (int c = 0; c < 3; c++) {
+      if (!nit[c]) continue;
+      const int ncd = c + 1;
+      dim3 g((nrows / BIL_R) * tb.nchunk, nit[c], (B * ncd + 2) / 3);
+      k_bilinear_packed<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L[c], ncd, row0,
+                                                                      S.act, S.nact);
+      launches++;
+    }
+  } else {
+    launch_bilinear_class<1>(tb, S, L[0], nit[0], row0, nrows, mask, st);
+    launch_bilinear_class<2>(tb, S, L[1], nit[1], row0, nrows, mask, st);
+    launch_bilinear_class<3>(tb, S, L[2], nit[2], row0, nrows, mask, st);
+    launches += (nit[0] > 0) + (nit[1] > 0) + (nit[2] > 0);
+  }
   RT_TOC(prof, st);
-  launches += (nit[0] > 0) + (nit[1] > 0) + (nit[2] > 0);
   if (groups & GRP_PMR) {
     RT_TIC(prof, PC_JLO, st);
     k_jlo<<<B, 256, tb.nsup * sizeof(double), st>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
@@ -469,6 +623,7 @@ int integrals_configure() {
   cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 1, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(k_bilinear_packed<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
 }
 

@@ -96,6 +96,7 @@ struct Batch {
   int *m_full_step, *m_full_acc, *m_out_int;  // masks of the integral launches
   long long *counters;     // [B][4]
   long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
+  int *act, *nact;         // [B], [1] compacted list of the cosmologies of the current launch
   int *n_active;           // [1]
   // outputs
   double *out;             // concatenated tables

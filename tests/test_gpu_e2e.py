@@ -134,3 +134,20 @@ def test_pinned_read_back_equals_copying_run(example1_dir):
     t3, *_ = h.run()
     assert np.array_equal(t3[1], t1[1])
     h.close()
+
+
+def test_packed_batch_kernel_is_bit_identical(example1_dir, example1_full_dir):
+    """Batches of >= 6 cosmologies go through k_bilinear_packed (three (cosmology, spectrum)
+    slots per CTA); the per-slot arithmetic is the same, so nothing may change."""
+    single, *_ = run(example1_dir)
+    single_full, *_ = run(example1_full_dir)
+    h = rt.RedTimeB200()
+    dirs = [example1_dir, example1_full_dir, example1_dir, example1_dir, example1_full_dir, example1_dir,
+            example1_dir]
+    h.add_cosmologies([rt.read_run_dir(d) for d in dirs])
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    assert not status.any()
+    for d, t in zip(dirs, tables):
+        assert np.array_equal(t, single if d == example1_dir else single_full)
+    h.close()
