@@ -1,0 +1,80 @@
+"""The drop-in boundary at process level and parity on cosmologies other than example 1.
+
+  * `redTime_b200` honours the reference's contract (scripts/runRedTime:196-229): no argv, reads
+    ./params_redTime.dat from the CWD, prints the tables to stdout.
+  * Latin-hypercube cosmologies (config 4 generator, all PRINT* column groups = 84 columns) run
+    through the batch API and, from the same run directories, through the oracle binary
+    `oracle/_ref/redTime_printall` (the unmodified reference with PRINTA=PRINTI=PRINTQ=PRINTBIAS=1)
+    on the host cores of the GPU box."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import redtime_b200 as rt
+from redtime_b200 import workload as wl
+from conftest import ORACLE_REF, ROOT, parse_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def test_executable_reproduces_golden_stdout(example1_dir, golden_example1):
+    exe = os.path.join(ROOT, "redtime_b200", "redTime_b200")
+    p = subprocess.run([exe], cwd=example1_dir, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    hdr, arr = parse_tables(p.stdout)
+    ghdr, gold = golden_example1
+    assert hdr == ghdr                      # banner + '###main' lines byte-identical
+    assert arr.shape == gold.shape
+    e = np.max(np.abs(arr - gold) / (np.abs(gold) + 1e-300), axis=0)
+    assert np.all(e[:7] < 1e-6) and np.all(e[7:15] < 1e-5), e
+    blocks = p.stdout.split("\n\n\n")       # two blank lines after every redshift block
+    assert len(blocks) == 8 and blocks[-1] == ""
+
+
+def test_executable_fails_cleanly_without_inputs(tmp_path):
+    exe = os.path.join(ROOT, "redtime_b200", "redTime_b200")
+    p = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode != 0 and "params_redTime.dat" in p.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ORACLE_REF, "redTime_printall")), reason="oracle/_ref not built")
+def test_latin_hypercube_cosmologies_all_columns(tmp_path):
+    base = wl.load_example1(subsample=27)   # ~570 rows: the scripts' default CAMB density
+    cosmos = wl.make_cosmologies(4, base, seed=wl.SEED + 1)
+    dirs = [wl.write_run_dir(str(tmp_path / ("M%03d" % i)), c) for i, c in enumerate(cosmos)]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    procs = [subprocess.Popen([os.path.join(ORACLE_REF, "redTime_printall")], cwd=d, env=env,
+                              stdout=open(os.path.join(d, "ref.dat"), "w")) for d in dirs]
+    h = rt.RedTimeB200(print_A=1, print_I=1, print_Q=1, print_bias=1)
+    h.add_cosmologies([rt.read_run_dir(d) for d in dirs])  # the same bytes the oracle reads
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    h.close()
+    assert not status.any()
+    assert all(p.wait(timeout=600) == 0 for p in procs)
+    for d, tab in zip(dirs, tables):
+        rhdr, ref = parse_tables(open(os.path.join(d, "ref.dat")).read())
+        ref = ref.reshape(tab.shape)
+        assert tab.shape[2] == 84
+        e = np.max(np.abs(tab - ref) / (np.abs(ref) + 1e-300), axis=(0, 1))
+        assert np.all(e[:7] < 1e-6), (d, e[:7])
+        assert np.all(e[7:10] < 1e-5), (d, e[7:10])
+        # optional groups: relative to the local scale of the column (sign changes) and away
+        # from the lowest-k cancellation rows
+        k = ref[0, :, 0]
+        a = np.abs(ref)
+        scale = a.copy()
+        for sh in (1, 2):
+            scale[:, sh:] = np.maximum(scale[:, sh:], a[:, :-sh])
+            scale[:, :-sh] = np.maximum(scale[:, :-sh], a[:, sh:])
+        hi = k > 5.7e-3
+        el = np.max(np.abs(tab[:, hi] - ref[:, hi]) / (scale[:, hi] + 1e-300), axis=(0, 1))
+        assert np.all(el[10:] < 1e-5), (d, el[10:])
+        # header lines: eta, a, z, H, sigma_v^2 to the 12 printed digits
+        p = os.path.join(d, "mine.dat")
+        i = dirs.index(d)
+        rt.print_result(p, 128, tab, hdr[i], hdr0[i])
+        mine = [l for l in open(p).read().split("\n") if l.startswith("#")]
+        assert mine == rhdr
