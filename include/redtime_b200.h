@@ -204,6 +204,8 @@ typedef struct rtrg_run_inputs rtrg_run_inputs;
 /* parse <dir>/params_redTime.dat and the CAMB files it names (hdr:231-353,547-627,790-832);
  * camb_modern != 0 selects the 13-column layout (hdr:76-80) */
 int rtrg_read_run_dir(const char *dir, int camb_modern, rtrg_run_inputs **out);
+/* n run directories at once, spread over the host threads; out[n] receives the handles */
+int rtrg_read_run_dirs(int n, const char *const *dirs, int camb_modern, rtrg_run_inputs **out);
 const rtrg_cosmology *rtrg_inputs_cosmology(const rtrg_run_inputs *in);
 void rtrg_free_run_inputs(rtrg_run_inputs *in);
 /* print one cosmology's result exactly as the reference's main() does (stdout format of

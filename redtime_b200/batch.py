@@ -41,7 +41,7 @@ def gpu_runner(run_dirs, device=0, **cfg):
     if not run_dirs:
         return {}
     h = rt.RedTimeB200(device=device, **cfg)
-    h.add_cosmologies([rt.read_run_dir(d) for d in run_dirs])
+    h.add_run_dirs(run_dirs)  # parallel parse (std::from_chars, one host thread per directory)
     h.prepare()
     tables, hdr, hdr0, status = h.run(raise_on_ode_failure=False)
     for i, d in enumerate(run_dirs):

@@ -98,6 +98,7 @@ def load_library():
     lib.rtrg_table_windows.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp]
     lib.rtrg_assembly_terms.argtypes = [_ip, _ip, _ip, _ip, _dp, C.c_int]
     lib.rtrg_read_run_dir.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rtrg_read_run_dirs.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
     lib.rtrg_inputs_cosmology.argtypes = [C.c_void_p]
     lib.rtrg_inputs_cosmology.restype = C.POINTER(_Cosmology)
     lib.rtrg_free_run_inputs.argtypes = [C.c_void_p]
@@ -292,6 +293,24 @@ class RedTimeB200:
         _check(self.lib.rtrg_add_cosmology(self.h, C.byref(c)))
         self._nout.append(int(c.n_out))
         return len(self._nout) - 1
+
+    def add_run_dirs(self, paths, camb_modern=False):
+        """Parse the run directories (params_redTime.dat + CAMB files) on the host threads of the
+        library and add them as one batch; no intermediate numpy copies."""
+        n = len(paths)
+        cpaths = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        hnd = (C.c_void_p * n)()
+        rc = self.lib.rtrg_read_run_dirs(n, cpaths, int(camb_modern), hnd)
+        if rc != 0:
+            raise RtrgError(rc, "cannot read one of the run directories")
+        try:
+            ptrs = [self.lib.rtrg_inputs_cosmology(hnd[i]) for i in range(n)]
+            arr = (C.POINTER(_Cosmology) * n)(*ptrs)
+            _check(self.lib.rtrg_add_cosmologies(self.h, n, arr))
+            self._nout.extend(int(p.contents.n_out) for p in ptrs)
+        finally:
+            for i in range(n):
+                self.lib.rtrg_free_run_inputs(hnd[i])
 
     def add_cosmologies(self, dicts):
         """Batch form of add_cosmology: one C-ABI call, table copies on several host threads."""

@@ -76,3 +76,26 @@ def test_printer_reproduces_the_reference_stdout(tmp_path, golden_example1):
     same = sum(a == b for a, b in zip(ml, rl))
     assert same >= 0.99 * len(rl)
     assert all(len(a) == len(b) for a, b in zip(ml, rl))
+
+
+def test_fast_parser_matches_numpy_loadtxt(example1_dir):
+    """SURVEY 8f-3: the std::from_chars ingestion must give the same doubles as a reference
+    text parser (numpy) for every CAMB column the path uses."""
+    d = rt.read_run_dir(example1_dir)
+    z0 = np.loadtxt(os.path.join(example1_dir, "camb_transfer_z0.dat"))
+    assert np.array_equal(z0[:, 0], d["k_T"]) and np.array_equal(z0[:, 1], d["Tc_T"]) and np.array_equal(z0[:, 2], d["Tb_T"])
+    for zs, iz in ((".5", 10), ("200", 0), ("3", 7)):
+        t = np.loadtxt(os.path.join(example1_dir, "camb_transfer_z%s.dat" % zs))
+        assert np.array_equal(t[:, 1], d["Tc_b"][iz]) and np.array_equal(t[:, 5], d["Tnu_b"][iz])
+
+
+def test_comment_lines_in_transfer_files(tmp_path):
+    base = wl.load_example1(subsample=256)
+    c = wl.make_cosmologies(1, base)[0]
+    d = wl.write_run_dir(str(tmp_path / "c"), c)
+    p = os.path.join(d, "camb_transfer_z0.dat")
+    rows = open(p).read().split("\n")
+    rows = ["# header", "# k/h  CDM  baryon ..."] + rows[:5] + ["# a comment between rows"] + rows[5:]
+    open(p, "w").write("\n".join(rows))
+    r = rt.read_run_dir(d)
+    assert np.array_equal(r["k_T"], c["k_T"]) and np.array_equal(r["Tb_T"], c["Tb_T"])
