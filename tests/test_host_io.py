@@ -90,12 +90,19 @@ def test_fast_parser_matches_numpy_loadtxt(example1_dir):
 
 
 def test_comment_lines_in_transfer_files(tmp_path):
+    """The z=0 transfer file may carry '#' lines between rows (hdr:805-821 discards them); the
+    interpolation files after the first are a plain token stream in the reference (hdr:596-622),
+    where a comment silently truncates the table -- here that is an error."""
     base = wl.load_example1(subsample=256)
     c = wl.make_cosmologies(1, base)[0]
     d = wl.write_run_dir(str(tmp_path / "c"), c)
-    p = os.path.join(d, "camb_transfer_z0.dat")
-    rows = open(p).read().split("\n")
+    rows = open(os.path.join(d, "camb_transfer_z0.dat")).read().split("\n")
     rows = ["# header", "# k/h  CDM  baryon ..."] + rows[:5] + ["# a comment between rows"] + rows[5:]
-    open(p, "w").write("\n".join(rows))
+    open(os.path.join(d, "transfer_T.dat"), "w").write("\n".join(rows))
+    par = open(os.path.join(d, "params_redTime.dat")).read().replace("camb_transfer_z0.dat", "transfer_T.dat")
+    open(os.path.join(d, "params_redTime.dat"), "w").write(par)
     r = rt.read_run_dir(d)
     assert np.array_equal(r["k_T"], c["k_T"]) and np.array_equal(r["Tb_T"], c["Tb_T"])
+    open(os.path.join(d, "camb_transfer_z3.dat"), "w").write("# comment\n" + open(os.path.join(d, "camb_transfer_z3.dat")).read())
+    with pytest.raises(rt.RtrgError):
+        rt.read_run_dir(d)
