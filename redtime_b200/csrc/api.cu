@@ -3,6 +3,9 @@
 // numerical result is produced by the CUDA kernels; there is no CPU execution path.
 #include <cuda_runtime.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -181,6 +184,79 @@ static void prof_collect(rtrg_handle *h) {
   h->profiler.reset();
 }
 
+// ---- on-disk cache of the cosmology-independent kernels T_n (24 MB at nk=128, 95 MB at
+// nk=256).  Building them takes ~1.3 s (5 s) of long-double FFTs on the host; the drop-in
+// executable is started once per model, so it reloads them instead.  RTRG_CACHE_DIR selects the
+// directory (default $XDG_CACHE_HOME/redtime_b200 or ~/.cache/redtime_b200; "off" disables).
+struct TableCacheHeader {
+  char magic[8];
+  int version, nk, np, nsup, n_tc, n_tlo, n_kfac, pad;
+  double kmin, kmax, kfac_lo, checksum;
+};
+static std::string table_cache_path(const GridSpec &g) {
+  const char *dir = std::getenv("RTRG_CACHE_DIR");
+  std::string d;
+  if (dir && *dir) {
+    if (std::string(dir) == "off") return "";
+    d = dir;
+  } else if (const char *x = std::getenv("XDG_CACHE_HOME")) {
+    d = std::string(x) + "/redtime_b200";
+  } else if (const char *hme = std::getenv("HOME")) {
+    d = std::string(hme) + "/.cache/redtime_b200";
+  } else {
+    return "";
+  }
+  char name[160];
+  std::snprintf(name, sizeof name, "/T_v1_nk%d_%.17g_%.17g.bin", g.nk, g.kmin, g.kmax);
+  return d + name;
+}
+static double table_checksum(const std::vector<double> &a, const std::vector<double> &b, const std::vector<double> &c) {
+  double s = 0;
+  for (const auto *v : {&a, &b, &c})
+    for (size_t i = 0; i < v->size(); i += 97) s += (*v)[i] * (double)(1 + i % 13);
+  return s;
+}
+static bool load_table_cache(const std::string &path, const GridSpec &g, std::vector<double> &Tc,
+                             std::vector<double> &Tlo, std::vector<double> &kfac, double *kfac_lo) {
+  if (path.empty()) return false;
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  TableCacheHeader h;
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTRGTAB", 8) == 0 && h.version == 1 &&
+            h.nk == g.nk && h.np == g.np && h.nsup == g.nsup && h.kmin == g.kmin && h.kmax == g.kmax &&
+            (size_t)h.n_tc == Tc.size() && (size_t)h.n_tlo == Tlo.size() && (size_t)h.n_kfac == kfac.size();
+  ok = ok && std::fread(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size();
+  ok = ok && std::fread(Tlo.data(), sizeof(double), Tlo.size(), f) == Tlo.size();
+  ok = ok && std::fread(kfac.data(), sizeof(double), kfac.size(), f) == kfac.size();
+  std::fclose(f);
+  ok = ok && table_checksum(Tc, Tlo, kfac) == h.checksum;
+  if (ok) *kfac_lo = h.kfac_lo;
+  else std::fill(Tc.begin(), Tc.end(), 0.0);
+  return ok;
+}
+static void save_table_cache(const std::string &path, const GridSpec &g, const std::vector<double> &Tc,
+                             const std::vector<double> &Tlo, const std::vector<double> &kfac, double kfac_lo) {
+  if (path.empty()) return;
+  const std::string dir = path.substr(0, path.rfind('/'));
+  for (size_t i = 1; i <= dir.size(); i++)  // mkdir -p
+    if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
+  const std::string tmp = path + ".tmp" + std::to_string((long long)::getpid());
+  FILE *f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  TableCacheHeader h;
+  std::memset(&h, 0, sizeof h);
+  std::memcpy(h.magic, "RTRGTAB", 8);
+  h.version = 1, h.nk = g.nk, h.np = g.np, h.nsup = g.nsup;
+  h.n_tc = (int)Tc.size(), h.n_tlo = (int)Tlo.size(), h.n_kfac = (int)kfac.size();
+  h.kmin = g.kmin, h.kmax = g.kmax, h.kfac_lo = kfac_lo, h.checksum = table_checksum(Tc, Tlo, kfac);
+  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size() &&
+            std::fwrite(Tlo.data(), sizeof(double), Tlo.size(), f) == Tlo.size() &&
+            std::fwrite(kfac.data(), sizeof(double), kfac.size(), f) == kfac.size();
+  ok = (std::fclose(f) == 0) && ok;
+  if (ok) std::rename(tmp.c_str(), path.c_str());  // atomic: concurrent writers cannot tear the file
+  else std::remove(tmp.c_str());
+}
+
 template <class T>
 static int dev_alloc(std::vector<void *> &pool, T **p, size_t n, bool zero = true) {
   void *q = nullptr;
@@ -296,7 +372,8 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   std::vector<double> Tc((size_t)N_JKERN * tb.NUp * tb.ldT, 0.0), kfac((size_t)N_JKERN * nk);
   std::vector<double> Tlo((size_t)g.nsup * g.nsup);
   double kfac_lo = 0;
-  {
+  const std::string cache = table_cache_path(g);
+  if (!load_table_cache(cache, g, Tc, Tlo, kfac, &kfac_lo)) {
     std::vector<std::thread> th;
     for (int n = 0; n < N_JKERN; n++)
       th.emplace_back([&, n]() {
@@ -323,6 +400,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
         }
       });
     for (auto &t : th) t.join();
+    save_table_cache(cache, g, Tc, Tlo, kfac, kfac_lo);
   }
   tb.kfac_lo = kfac_lo;
   std::vector<double> G((size_t)N_ZKERN * (2 * np - 1));

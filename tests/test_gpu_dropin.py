@@ -78,3 +78,30 @@ def test_latin_hypercube_cosmologies_all_columns(tmp_path):
         rt.print_result(p, 128, tab, hdr[i], hdr0[i])
         mine = [l for l in open(p).read().split("\n") if l.startswith("#")]
         assert mine == rhdr
+
+
+def test_table_cache_round_trip(tmp_path, example1_dir, stage_golden_1loop, monkeypatch):
+    """The cosmology-independent kernels T_n are cached on disk (RTRG_CACHE_DIR); a handle
+    created from the cache must give bit-identical integrals."""
+    import time
+    monkeypatch.setenv("RTRG_CACHE_DIR", str(tmp_path / "cache"))
+    g = stage_golden_1loop
+    res, dt = [], []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        h = rt.RedTimeB200()
+        dt.append(time.perf_counter() - t0)
+        h.add_cosmology(rt.read_run_dir(example1_dir))
+        h.prepare()
+        res.append(h.integrals_raw(g["yp"][:3 * 128]))
+        h.close()
+    files = os.listdir(str(tmp_path / "cache"))
+    assert len(files) == 1 and files[0].startswith("T_v1_nk128_")
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert np.array_equal(a, b)
+    assert res[0][3] == res[1][3]
+    assert dt[1] < dt[0]
+    monkeypatch.setenv("RTRG_CACHE_DIR", "off")
+    h = rt.RedTimeB200()
+    h.close()
+    assert len(os.listdir(str(tmp_path / "cache"))) == 1
