@@ -105,3 +105,27 @@ def test_table_cache_round_trip(tmp_path, example1_dir, stage_golden_1loop, monk
     h = rt.RedTimeB200()
     h.close()
     assert len(os.listdir(str(tmp_path / "cache"))) == 1
+
+
+def test_emulator_goldens_massless_neutrinos(tmp_path):
+    """The reference's own goldens M001-M010 (massless neutrinos, w0wa; genuine GSL): k, D, f and
+    the header H.  Also exercises the n_z = 0 path (Beta_P == 0) and linear-only switches."""
+    import re
+    from test_oracle_golden import emulator_kat, write_massless_run_dir
+    kat = emulator_kat()
+    dirs = [write_massless_run_dir(str(tmp_path / m), kat[m]) for m in sorted(kat)]
+    h = rt.RedTimeB200()
+    h.add_run_dirs(dirs)
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    h.close()
+    assert not status.any()
+    for m, tab, hd in zip(sorted(kat), tables, hdr):
+        rec = kat[m]
+        assert tab.shape == (8, 128, 10)   # k, 6 linear columns, P_dd, P_dt, P_tt (print_rsd = 0)
+        for i in range(8):
+            assert np.max(np.abs(tab[i, :, 0] / np.array(rec["k"]) - 1)) < 1e-11   # 12 printed digits
+            assert np.max(np.abs(tab[i, :, 1] / rec["D"][i] - 1)) < 1e-11, m
+            assert np.max(np.abs(tab[i, :, 2] / rec["f"][i] - 1)) < 1e-11, m
+            assert abs(hd[i, 3] / rec["H"][i] - 1) < 1e-11
+            assert not tab[i, :, 4:7].any()
