@@ -3,6 +3,7 @@
 // numerical result is produced by the CUDA kernels; there is no CPU execution path.
 #include <cuda_runtime.h>
 
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -552,6 +553,23 @@ int rtrg_num_columns(const rtrg_handle *h, int i) {
   return num_columns(h->cfg, h->cos[i].c);
 }
 
+// host threads one handle may use for staging: RTRG_HOST_THREADS, else the cores this process
+// may run on divided by the ranks of the node (LOCAL_WORLD_SIZE, set by torchrun), capped
+static int host_threads(int cap) {
+  if (const char *v = std::getenv("RTRG_HOST_THREADS")) {
+    const int n = std::atoi(v);
+    if (n > 0) return std::min(n, 64);
+  }
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::min(n, (int)CPU_COUNT(&set));
+  if (const char *w = std::getenv("LOCAL_WORLD_SIZE")) {
+    const int ws = std::atoi(w);
+    if (ws > 1) n = n / ws;
+  }
+  return std::max(1, std::min(n, cap));
+}
+
 static int check_cosmology(const rtrg_cosmology *in) {
   if (!in) return fail(RTRG_EINVAL, "null cosmology");
   if (in->n_out < 1 || in->n_out > RTRG_MAX_OUT || !in->z_out) return fail(RTRG_EINVAL, "bad n_out");
@@ -639,8 +657,8 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     h->d_in_uploaded = 0;  // the staged prefix goes out again with the first chunk
   }
   // parallel staging: the copies are memory-bound, one thread saturates only ~10 GB/s
-  int nth = (int)std::thread::hardware_concurrency();
-  nth = std::max(1, std::min(std::min(nth, 16), n));
+  int nth = host_threads(16);
+  nth = std::max(1, std::min(nth, n));
   double *base = h->stage.base;
   const int chunk = std::max(nth, 64);
   for (int c0 = 0; c0 < n; c0 += chunk) {
