@@ -9,8 +9,8 @@ library or a CUDA device is missing.
 from .binding import (RedTimeB200, RtrgError, Config, load_library, library_path,
                       read_run_dir, grid_info, table_T, table_G, table_windows,
                       assembly_terms, print_result, dfma_peak_tflops, kshard_nccl_id,
-                      LoopbackGroup)
+                      LoopbackGroup, pack_cosmologies)
 
 __all__ = ["RedTimeB200", "RtrgError", "Config", "load_library", "library_path",
            "read_run_dir", "grid_info", "table_T", "table_G", "table_windows",
-           "assembly_terms", "print_result", "dfma_peak_tflops", "kshard_nccl_id", "LoopbackGroup"]
+           "assembly_terms", "print_result", "dfma_peak_tflops", "kshard_nccl_id", "LoopbackGroup", "pack_cosmologies"]

@@ -227,6 +227,19 @@ class LoopbackGroup:
             self.g = None
 
 
+class PackedCosmologies:
+    """ctypes view of a list of cosmology dicts, reusable across add_cosmologies() calls."""
+
+    def __init__(self, dicts):
+        self.structs = [RedTimeB200._struct(d) for d in dicts]
+        self.array = (C.POINTER(_Cosmology) * len(self.structs))(*[C.pointer(c) for c, _ in self.structs])
+        self.n_out = [int(c.n_out) for c, _ in self.structs]
+
+
+def pack_cosmologies(dicts):
+    return PackedCosmologies(dicts)
+
+
 def dfma_peak_tflops(device=0, seconds=0.5):
     """Measured FP64 FMA peak of the device (TFLOP/s)."""
     lib = load_library()
@@ -313,11 +326,13 @@ class RedTimeB200:
                 self.lib.rtrg_free_run_inputs(hnd[i])
 
     def add_cosmologies(self, dicts):
-        """Batch form of add_cosmology: one C-ABI call, table copies on several host threads."""
-        structs = [self._struct(d) for d in dicts]
-        arr = (C.POINTER(_Cosmology) * len(structs))(*[C.pointer(c) for c, _ in structs])
-        _check(self.lib.rtrg_add_cosmologies(self.h, len(structs), arr))
-        self._nout.extend(int(c.n_out) for c, _ in structs)
+        """Batch form of add_cosmology: one C-ABI call, table copies on several host threads
+        (page-locked arrays are sent to the device directly, see include/redtime_b200.h).
+        `dicts` may also be the result of pack_cosmologies(), which skips the struct building."""
+        pack = dicts if isinstance(dicts, PackedCosmologies) else pack_cosmologies(dicts)
+        _check(self.lib.rtrg_add_cosmologies(self.h, len(pack.structs), pack.array))
+        self._nout.extend(pack.n_out)
+        self._keep = [pack]  # page-locked buffers must outlive rtrg_prepare
 
     @property
     def n_cosmo(self):

@@ -72,8 +72,13 @@ static int fail(int code, const char *fmt, ...) {
   } while (0)
 
 struct HostCosmo {
-  Cosmo c;  // offsets point into the staging arena (= the device input pool)
+  Cosmo c;  // offsets point into the device input pool
   std::vector<double> z_out;
+  size_t stage_off = 0, stage_len = 0;  // this cosmology's slice of the staging arena
+  size_t dev_len = 0;                   // ... and of the device pool (starts at c.offT)
+  // page-locked caller buffers are sent as they are (no host copy): k_T, Tc_T, Tb_T, k_b, Tnu_b, Tc_b
+  bool direct = false;
+  const double *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // Pinned host arena mirroring the device input pool: rtrg_add_cosmology copies the caller's
@@ -126,7 +131,7 @@ struct rtrg_handle {
   StagingArena stage;
   DeviceArena work;
   double *d_in = nullptr;     // device input pool (mirror of stage)
-  size_t d_in_cap = 0, d_in_uploaded = 0;
+  size_t d_in_cap = 0, d_in_used = 0;
   bool d_in_transformed = false;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_done = nullptr;
@@ -540,7 +545,7 @@ int rtrg_clear_cosmologies(rtrg_handle *h) {
   h->cos.clear();
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   h->stage.used = 0;
-  h->d_in_uploaded = 0;
+  h->d_in_used = 0;
   h->d_in_transformed = false;
   h->prepared = h->uploaded = false;
   return RTRG_OK;
@@ -579,12 +584,17 @@ static int check_cosmology(const rtrg_cosmology *in) {
     return fail(RTRG_EINVAL, "bad interpolation tables");
   return RTRG_OK;
 }
-static size_t cosmology_doubles(const rtrg_cosmology *in) {
-  const size_t nz = in->n_z > 0 ? in->n_z : 0, nkb = in->n_z > 0 ? in->n_kb : 0;
-  return 3 * (size_t)in->n_T + nz + nkb + nz * nkb;
+static bool is_page_locked(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
 }
-// scalars + offsets of one cosmology whose tables start at arena offset `off`
-static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off) {
+// scalars + layout of one cosmology whose tables start at device-pool offset `off` and
+// staging-arena offset `soff`
+static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off, size_t soff) {
   HostCosmo hc;
   Cosmo &c = hc.c;
   std::memset(&c, 0, sizeof c);
@@ -605,58 +615,108 @@ static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off) {
   c.offA = (long long)(off + 3 * nT);
   c.offKb = (long long)(off + 3 * nT + nz);
   c.offB = (long long)(off + 3 * nT + nz + nkb);
+  c.offTc = -1;
+  hc.dev_len = 3 * nT + nz + nkb + nz * nkb;
+  hc.direct = is_page_locked(in->k_T) && is_page_locked(in->Tc_T) && is_page_locked(in->Tb_T) &&
+              (nz == 0 || (is_page_locked(in->k_b) && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b)));
+  hc.stage_off = soff;
+  if (hc.direct) {
+    hc.src[0] = in->k_T, hc.src[1] = in->Tc_T, hc.src[2] = in->Tb_T;
+    hc.src[3] = in->k_b, hc.src[4] = in->Tnu_b, hc.src[5] = in->Tc_b;
+    if (nz) c.offTc = (long long)(off + hc.dev_len);
+    hc.dev_len += nz * nkb;
+    hc.stage_len = nz;  // only the a nodes are formed on the host
+  } else {
+    hc.stage_len = hc.dev_len;
+  }
   return hc;
 }
 // copy the caller's tables into the staging arena (the z=0 columns raw, beta formed here)
-static void stage_cosmology(const rtrg_cosmology *in, const Cosmo &c, double *base) {
+static void stage_cosmology(const rtrg_cosmology *in, const HostCosmo &hc, double *base) {
+  const Cosmo &c = hc.c;
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
-  std::memcpy(base + c.offT, in->k_T, nT * sizeof(double));
-  std::memcpy(base + c.offLT, in->Tc_T, nT * sizeof(double));
-  std::memcpy(base + c.offTb, in->Tb_T, nT * sizeof(double));
-  for (size_t i = 0; i < nz; i++) base[c.offA + i] = 1.0 / (1.0 + in->z_interp[i]);
+  double *s = base + hc.stage_off;
+  if (hc.direct) {
+    for (size_t i = 0; i < nz; i++) s[i] = 1.0 / (1.0 + in->z_interp[i]);
+    return;
+  }
+  std::memcpy(s, in->k_T, nT * sizeof(double));
+  std::memcpy(s + nT, in->Tc_T, nT * sizeof(double));
+  std::memcpy(s + 2 * nT, in->Tb_T, nT * sizeof(double));
+  for (size_t i = 0; i < nz; i++) s[3 * nT + i] = 1.0 / (1.0 + in->z_interp[i]);
   if (nz) {
-    std::memcpy(base + c.offKb, in->k_b, nkb * sizeof(double));
+    std::memcpy(s + 3 * nT + nz, in->k_b, nkb * sizeof(double));
     // beta = f_nu T_nu / T_c (hdr:556-623), formed on the fly: halves the bytes that cross PCIe
     const double fn = c.On / c.Om;
     const double *tn = in->Tnu_b, *tc = in->Tc_b;
-    double *dst = base + c.offB;
+    double *dst = s + 3 * nT + nz + nkb;
     const size_t n = nz * nkb;
     for (size_t i = 0; i < n; i++) dst[i] = fn * tn[i] / tc[i];
   }
 }
+// host -> device copies of one cosmology on the copy stream
+static int upload_cosmology(rtrg_handle *h, const HostCosmo &hc) {
+  const Cosmo &c = hc.c;
+  cudaStream_t cs = h->copy_stream;
+  const double *s = h->stage.base + hc.stage_off;
+  if (!hc.direct) {
+    CU(cudaMemcpyAsync(h->d_in + c.offT, s, hc.stage_len * sizeof(double), cudaMemcpyHostToDevice, cs));
+    return RTRG_OK;
+  }
+  const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
+  CU(cudaMemcpyAsync(h->d_in + c.offT, hc.src[0], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
+  CU(cudaMemcpyAsync(h->d_in + c.offLT, hc.src[1], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
+  CU(cudaMemcpyAsync(h->d_in + c.offTb, hc.src[2], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
+  if (nz) {
+    CU(cudaMemcpyAsync(h->d_in + c.offA, s, nz * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(h->d_in + c.offKb, hc.src[3], nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(h->d_in + c.offB, hc.src[4], nz * nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(h->d_in + c.offTc, hc.src[5], nz * nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
+  }
+  return RTRG_OK;
+}
 
 int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *list) {
   if (!h || n < 0 || (n > 0 && !list)) return fail(RTRG_EINVAL, "null argument");
-  size_t need = h->stage.used;
   for (int i = 0; i < n; i++) {
     int rc = check_cosmology(list[i]);
     if (rc) return rc;
-    need += cosmology_doubles(list[i]);
   }
   CU(cudaSetDevice(h->cfg.device));
-  if (need > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
-  if (h->stage.reserve(need) != RTRG_OK) return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", need * sizeof(double));
   const size_t first = h->cos.size();
-  size_t off = h->stage.used;
+  size_t off = h->d_in_used, soff = h->stage.used;
   for (int i = 0; i < n; i++) {
-    h->cos.push_back(describe_cosmology(list[i], off));
-    off += cosmology_doubles(list[i]);
+    h->cos.push_back(describe_cosmology(list[i], off, soff));
+    off += h->cos.back().dev_len;
+    soff += h->cos.back().stage_len;
   }
-  h->stage.used = off;
-  // device pool large enough? then each staged chunk is sent right away on the copy stream,
-  // overlapping the PCIe transfer with the staging of the next chunk
-  if (h->stage.used > h->d_in_cap) {
+  if (soff > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
+  if (h->stage.reserve(soff) != RTRG_OK) {
+    h->cos.resize(first);
+    return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", soff * sizeof(double));
+  }
+  h->stage.used = soff;
+  h->d_in_used = off;
+  bool resend_prefix = false;
+  if (h->d_in_used > h->d_in_cap) {
     CU(cudaStreamSynchronize(h->copy_stream));
     double *q = nullptr;
-    const size_t ncap = h->stage.used + h->stage.used / 8;
+    const size_t ncap = h->d_in_used + h->d_in_used / 8;
     cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
     if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
     if (h->d_in) cudaFree(h->d_in);
     h->d_in = q;
     h->d_in_cap = ncap;
-    h->d_in_uploaded = 0;  // the staged prefix goes out again with the first chunk
+    resend_prefix = first > 0;
   }
-  // parallel staging: the copies are memory-bound, one thread saturates only ~10 GB/s
+  if (resend_prefix)
+    for (size_t b = 0; b < first; b++) {
+      int rc = upload_cosmology(h, h->cos[b]);
+      if (rc) return rc;
+    }
+  // Staging runs on several host threads (the copies are memory-bound, one thread moves only
+  // ~10 GB/s); every chunk is sent as soon as it is staged, so the PCIe transfer overlaps the
+  // staging of the next chunk.  Page-locked caller buffers skip the staging altogether.
   int nth = host_threads(16);
   nth = std::max(1, std::min(nth, n));
   double *base = h->stage.base;
@@ -664,20 +724,31 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int c1 = std::min(n, c0 + chunk);
     if (nth == 1) {
-      for (int i = c0; i < c1; i++) stage_cosmology(list[i], h->cos[first + i].c, base);
+      for (int i = c0; i < c1; i++) stage_cosmology(list[i], h->cos[first + i], base);
     } else {
       std::vector<std::thread> th;
       for (int t = 0; t < nth; t++)
         th.emplace_back([=]() {
-          for (int i = c0 + t; i < c1; i += nth) stage_cosmology(list[i], h->cos[first + i].c, base);
+          for (int i = c0 + t; i < c1; i += nth) stage_cosmology(list[i], h->cos[first + i], base);
         });
       for (auto &t : th) t.join();
     }
-    const size_t upto = (c1 == n) ? h->stage.used : (size_t)h->cos[first + c1].c.offT;
-    if (upto > h->d_in_uploaded) {
-      CU(cudaMemcpyAsync(h->d_in + h->d_in_uploaded, base + h->d_in_uploaded,
-                         (upto - h->d_in_uploaded) * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-      h->d_in_uploaded = upto;
+    // consecutive staged cosmologies are contiguous in the arena and in the pool: one copy
+    int i = c0;
+    while (i < c1) {
+      const HostCosmo &hc = h->cos[first + i];
+      if (hc.direct) {
+        int rc = upload_cosmology(h, hc);
+        if (rc) return rc;
+        i++;
+        continue;
+      }
+      int j = i;
+      size_t len = 0;
+      while (j < c1 && !h->cos[first + j].direct) len += h->cos[first + j++].stage_len;
+      CU(cudaMemcpyAsync(h->d_in + hc.c.offT, base + hc.stage_off, len * sizeof(double), cudaMemcpyHostToDevice,
+                         h->copy_stream));
+      i = j;
     }
   }
   h->prepared = h->uploaded = false;
@@ -834,10 +905,11 @@ int rtrg_prepare(rtrg_handle *h) {
   CU(cudaMemsetAsync(h->work.base, 0, h->work.used, st));
   // --- input pool: rtrg_add_cosmologies already sent the staged tables on the copy stream.  A
   // repeated rtrg_prepare (the log transform below consumed the raw columns) sends them again.
-  if (h->d_in_transformed) {
-    CU(cudaMemcpyAsync(h->d_in, h->stage.base, h->stage.used * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-    h->d_in_uploaded = h->stage.used;
-  }
+  if (h->d_in_transformed)
+    for (const HostCosmo &hc : h->cos) {
+      int rc = upload_cosmology(h, hc);
+      if (rc) return rc;
+    }
   CU(cudaEventRecord(h->copy_done, h->copy_stream));
   CU(cudaStreamWaitEvent(st, h->copy_done, 0));
   h->d_in_transformed = true;

@@ -37,6 +37,7 @@ __device__ __forceinline__ double slot_k(const Batch &S, const double *kgrid, in
 
 // In-place transform of the raw z=0 transfer columns (once per upload):
 //   k_T -> ln k;  Tc_T -> ln(T_cb / T_cb[0]) with T_cb = f_b T_b + f_c T_c  (hdr:804-823)
+//   T_nu -> beta = f_nu T_nu / T_c where the tables came in raw                (hdr:556-623)
 __global__ void k_prep_T0(Batch S, double *__restrict__ T0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= S.B) return;
@@ -52,6 +53,12 @@ __global__ void k_prep_inputs(Batch S, const double *__restrict__ T0) {
     const double Ti = f_b * S.in[c.offTb + i] + f_c * S.in[c.offLT + i];
     S.in[c.offT + i] = log(S.in[c.offT + i]);
     S.in[c.offLT + i] = log(Ti / t0);
+  }
+  if (c.offTc >= 0) {  // raw upload from page-locked caller buffers: beta = f_nu T_nu / T_c
+    const double fn = c.On / c.Om;
+    const long long nB = (long long)c.n_z * c.n_kb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nB; i += (long long)gridDim.x * blockDim.x)
+      S.in[c.offB + i] = fn * S.in[c.offB + i] / S.in[c.offTc + i];
   }
 }
 int launch_prep_inputs(const Batch &S, double *T0, int max_rows, cudaStream_t st, Profiler *prof) {

@@ -42,7 +42,9 @@ struct Cosmo {
   int n_z, n_kb;      // beta table a-nodes x k-nodes
   long long offA;     // a nodes = 1/(1+z_interp)
   long long offKb;    // k nodes of the interpolation files
-  long long offB;     // beta = f_nu T_nu / T_c [n_z][n_kb]  (hdr:556-623; formed while staging)
+  long long offB;     // beta = f_nu T_nu / T_c [n_z][n_kb]  (hdr:556-623): formed while staging, or
+                      // (page-locked caller buffers, sent as they are) T_nu here until
+  long long offTc;    // k_prep_inputs divides by the raw T_c stored at offTc; -1 when staged
   // results of the device-side initialisation
   double Norm;        // sigma_8 normalisation (hdr:874)
   double sigv2_0;     // sigma_v^2(z=0)       (hdr:961)

@@ -62,10 +62,26 @@ def latin_hypercube(n, seed=SEED):
     return u, rng.uniform(-0.02, 0.02, size=n)
 
 
-def make_cosmologies(n, base, seed=SEED, switches=(1, 1, 1, 1), z_out=REDSHIFTS_CE, z_in=200.0):
-    """n cosmologies (list of add_cosmology dicts) sharing base's table shapes."""
+def _pinned_like(a):
+    """Page-locked copy of array a (torch owns the allocation; numpy views it)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    v.setflags(write=True)
+    return v
+
+
+def make_cosmologies(n, base, seed=SEED, switches=(1, 1, 1, 1), z_out=REDSHIFTS_CE, z_in=200.0, pinned=False):
+    """n cosmologies (list of add_cosmology dicts) sharing base's table shapes.  pinned=True puts
+    every table in page-locked host memory (needs a CUDA device): the library then sends them to
+    the GPU without a host-side copy."""
     u, eps = latin_hypercube(n, seed)
     out = []
+    if pinned:
+        base = dict(base)
+        for key in ("k_T", "k_b"):
+            base[key] = _pinned_like(base[key])
     tilt_T = base["k_T"] / 0.05
     tilt_b = base["k_b"] / 0.05
     for i in range(n):
@@ -74,11 +90,15 @@ def make_cosmologies(n, base, seed=SEED, switches=(1, 1, 1, 1), z_out=REDSHIFTS_
         wa = -(x ** 4) - w0
         params = np.array([ns, s8, h, om_m / h ** 2, om_b / h ** 2, om_nu / h ** 2, T_CMB, w0, wa])
         tT, tb = tilt_T ** eps[i], tilt_b ** eps[i]
-        out.append(dict(params=params, switches=list(switches), z_in=float(z_in),
-                        z_out=np.array(z_out, dtype=float), k_T=base["k_T"],
-                        Tc_T=base["Tc_T"] * tT, Tb_T=base["Tb_T"] * tT,
-                        z_interp=base["z_interp"], k_b=base["k_b"],
-                        Tc_b=base["Tc_b"] * tb[None, :], Tnu_b=base["Tnu_b"] * tb[None, :]))
+        c = dict(params=params, switches=list(switches), z_in=float(z_in),
+                 z_out=np.array(z_out, dtype=float), k_T=base["k_T"],
+                 Tc_T=base["Tc_T"] * tT, Tb_T=base["Tb_T"] * tT,
+                 z_interp=base["z_interp"], k_b=base["k_b"],
+                 Tc_b=base["Tc_b"] * tb[None, :], Tnu_b=base["Tnu_b"] * tb[None, :])
+        if pinned:
+            for key in ("Tc_T", "Tb_T", "Tc_b", "Tnu_b"):
+                c[key] = _pinned_like(c[key])
+        out.append(c)
     return out
 
 

@@ -151,3 +151,29 @@ def test_packed_batch_kernel_is_bit_identical(example1_dir, example1_full_dir):
     for d, t in zip(dirs, tables):
         assert np.array_equal(t, single if d == example1_dir else single_full)
     h.close()
+
+
+def test_page_locked_inputs_take_the_direct_path(example1_dir):
+    """Tables in page-locked memory are DMA'd as they are and beta is formed on the device;
+    pageable ones are staged with beta formed on the host.  IEEE division on both sides: the
+    results must be bit-identical, also in a batch that mixes the two and after a re-prepare."""
+    import torch
+    base = rt.read_run_dir(example1_dir)
+    pinned = dict(base)
+    keep = []
+    for key in ("k_T", "Tc_T", "Tb_T", "k_b", "Tc_b", "Tnu_b"):
+        t = torch.empty(base[key].shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = base[key]
+        keep.append(t)
+        pinned[key] = t.numpy()
+    h = rt.RedTimeB200()
+    h.add_cosmologies([base, pinned, base, pinned])
+    h.prepare()
+    tables, hdr, hdr0, status = h.run()
+    assert not status.any()
+    for t in tables[1:]:
+        assert np.array_equal(t, tables[0])
+    h.prepare()
+    again, *_ = h.run()
+    assert np.array_equal(again[1], tables[0]) and np.array_equal(again[2], tables[0])
+    h.close()

@@ -8,7 +8,7 @@ import redtime_b200 as rt
 from redtime_b200 import workload as wl
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 base = wl.load_example1()
-cos = wl.make_cosmologies(B, base)
+cos = rt.pack_cosmologies(wl.make_cosmologies(B, base, pinned=(len(sys.argv) > 2 and sys.argv[2] == "pinned")))
 h = rt.RedTimeB200()
 for it in range(3):
     t0 = time.perf_counter(); h.clear(); t1 = time.perf_counter()
