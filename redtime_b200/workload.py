@@ -68,7 +68,6 @@ def _pinned_like(a):
     t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
     v = t.numpy()
     v[...] = a
-    v.setflags(write=True)
     return v
 
 
