@@ -88,9 +88,9 @@ int rtrg_destroy(rtrg_handle *h);
 int rtrg_set_stream(rtrg_handle *h, void *cuda_stream);
 
 /* rtrg_add_cosmology copies the tables, so the caller's buffers may be freed right after the
- * call -- EXCEPT when k_T, Tc_T, Tb_T, k_b, Tc_b and Tnu_b of a cosmology are all page-locked
+ * call -- EXCEPT the two big interpolation tables Tc_b and Tnu_b when both are page-locked
  * (cudaHostAlloc / cudaHostRegister / torch pin_memory): those are sent to the device directly
- * with asynchronous copies, without a host-side copy, and must stay valid and unchanged until
+ * by the copy engine, without a host-side copy, and must stay valid and unchanged until
  * rtrg_prepare() has returned (and for every later rtrg_prepare() on the same batch).        */
 int rtrg_clear_cosmologies(rtrg_handle *h);
 int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *c);

@@ -74,11 +74,11 @@ static int fail(int code, const char *fmt, ...) {
 struct HostCosmo {
   Cosmo c;  // offsets point into the device input pool
   std::vector<double> z_out;
-  size_t stage_off = 0, stage_len = 0;  // this cosmology's slice of the staging arena
-  size_t dev_len = 0;                   // ... and of the device pool (starts at c.offT)
-  // page-locked caller buffers are sent as they are (no host copy): k_T, Tc_T, Tb_T, k_b, Tnu_b, Tc_b
+  size_t stage_off = 0, stage_len = 0;  // slice of the staging arena = slice of the pool at c.offT
+  // page-locked interpolation tables are sent as they are (no host copy): T_nu, T_c
   bool direct = false;
-  const double *src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t big_len = 0;
+  const double *src[2] = {nullptr, nullptr};
 };
 
 // Pinned host arena mirroring the device input pool: rtrg_add_cosmology copies the caller's
@@ -592,8 +592,10 @@ static bool is_page_locked(const void *p) {
   }
   return at.type == cudaMemoryTypeHost;
 }
-// scalars + layout of one cosmology whose tables start at device-pool offset `off` and
-// staging-arena offset `soff`
+// Scalars + layout of one cosmology.  Its "small" tables (k_T, Tc_T, Tb_T, a, k_b -- and beta
+// when it is formed on the host) start at device-pool offset `off` = staging-arena offset `soff`
+// region; the two big raw tables of a direct cosmology (T_nu, T_c of the interpolation files)
+// are placed by the caller afterwards (place_big).
 static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off, size_t soff) {
   HostCosmo hc;
   Cosmo &c = hc.c;
@@ -616,37 +618,30 @@ static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off, size_t
   c.offKb = (long long)(off + 3 * nT + nz);
   c.offB = (long long)(off + 3 * nT + nz + nkb);
   c.offTc = -1;
-  hc.dev_len = 3 * nT + nz + nkb + nz * nkb;
-  hc.direct = is_page_locked(in->k_T) && is_page_locked(in->Tc_T) && is_page_locked(in->Tb_T) &&
-              (nz == 0 || (is_page_locked(in->k_b) && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b)));
+  hc.direct = nz > 0 && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b);
   hc.stage_off = soff;
-  if (hc.direct) {
-    hc.src[0] = in->k_T, hc.src[1] = in->Tc_T, hc.src[2] = in->Tb_T;
-    hc.src[3] = in->k_b, hc.src[4] = in->Tnu_b, hc.src[5] = in->Tc_b;
-    if (nz) c.offTc = (long long)(off + hc.dev_len);
-    hc.dev_len += nz * nkb;
-    hc.stage_len = nz;  // only the a nodes are formed on the host
-  } else {
-    hc.stage_len = hc.dev_len;
-  }
+  hc.stage_len = 3 * nT + nz + nkb + (hc.direct ? 0 : nz * nkb);
+  hc.big_len = hc.direct ? 2 * nz * nkb : 0;
+  if (hc.direct) hc.src[0] = in->Tnu_b, hc.src[1] = in->Tc_b;
   return hc;
 }
-// copy the caller's tables into the staging arena (the z=0 columns raw, beta formed here)
+static void place_big(HostCosmo &hc, size_t off_big) {
+  if (!hc.direct) return;
+  hc.c.offB = (long long)off_big;
+  hc.c.offTc = (long long)(off_big + (size_t)hc.c.n_z * hc.c.n_kb);
+}
+// copy the caller's small tables into the staging arena; pageable interpolation tables are
+// reduced to beta = f_nu T_nu / T_c on the way (hdr:556-623), which halves their PCIe bytes
 static void stage_cosmology(const rtrg_cosmology *in, const HostCosmo &hc, double *base) {
   const Cosmo &c = hc.c;
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
   double *s = base + hc.stage_off;
-  if (hc.direct) {
-    for (size_t i = 0; i < nz; i++) s[i] = 1.0 / (1.0 + in->z_interp[i]);
-    return;
-  }
   std::memcpy(s, in->k_T, nT * sizeof(double));
   std::memcpy(s + nT, in->Tc_T, nT * sizeof(double));
   std::memcpy(s + 2 * nT, in->Tb_T, nT * sizeof(double));
   for (size_t i = 0; i < nz; i++) s[3 * nT + i] = 1.0 / (1.0 + in->z_interp[i]);
-  if (nz) {
-    std::memcpy(s + 3 * nT + nz, in->k_b, nkb * sizeof(double));
-    // beta = f_nu T_nu / T_c (hdr:556-623), formed on the fly: halves the bytes that cross PCIe
+  if (nz) std::memcpy(s + 3 * nT + nz, in->k_b, nkb * sizeof(double));
+  if (nz && !hc.direct) {
     const double fn = c.On / c.Om;
     const double *tn = in->Tnu_b, *tc = in->Tc_b;
     double *dst = s + 3 * nT + nz + nkb;
@@ -654,24 +649,32 @@ static void stage_cosmology(const rtrg_cosmology *in, const HostCosmo &hc, doubl
     for (size_t i = 0; i < n; i++) dst[i] = fn * tn[i] / tc[i];
   }
 }
-// host -> device copies of one cosmology on the copy stream
-static int upload_cosmology(rtrg_handle *h, const HostCosmo &hc) {
-  const Cosmo &c = hc.c;
-  cudaStream_t cs = h->copy_stream;
-  const double *s = h->stage.base + hc.stage_off;
-  if (!hc.direct) {
-    CU(cudaMemcpyAsync(h->d_in + c.offT, s, hc.stage_len * sizeof(double), cudaMemcpyHostToDevice, cs));
-    return RTRG_OK;
+// host -> device copies of the big raw tables of one direct cosmology, straight from the
+// caller's page-locked buffers
+static int upload_big(rtrg_handle *h, const HostCosmo &hc) {
+  if (!hc.direct) return RTRG_OK;
+  const size_t n = (size_t)hc.c.n_z * hc.c.n_kb * sizeof(double);
+  CU(cudaMemcpyAsync(h->d_in + hc.c.offB, hc.src[0], n, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->d_in + hc.c.offTc, hc.src[1], n, cudaMemcpyHostToDevice, h->copy_stream));
+  return RTRG_OK;
+}
+// (re-)send everything of the cosmologies [b0, b1)
+static int upload_range(rtrg_handle *h, size_t b0, size_t b1) {
+  if (b0 >= b1) return RTRG_OK;
+  // small tables: each add call left one contiguous slice in the arena and in the pool
+  size_t i = b0;
+  while (i < b1) {
+    size_t j = i, len = 0;
+    while (j < b1 && h->cos[j].c.offT == h->cos[i].c.offT + (long long)len &&
+           h->cos[j].stage_off == h->cos[i].stage_off + len)
+      len += h->cos[j++].stage_len;
+    CU(cudaMemcpyAsync(h->d_in + h->cos[i].c.offT, h->stage.base + h->cos[i].stage_off, len * sizeof(double),
+                       cudaMemcpyHostToDevice, h->copy_stream));
+    i = j;
   }
-  const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
-  CU(cudaMemcpyAsync(h->d_in + c.offT, hc.src[0], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
-  CU(cudaMemcpyAsync(h->d_in + c.offLT, hc.src[1], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
-  CU(cudaMemcpyAsync(h->d_in + c.offTb, hc.src[2], nT * sizeof(double), cudaMemcpyHostToDevice, cs));
-  if (nz) {
-    CU(cudaMemcpyAsync(h->d_in + c.offA, s, nz * sizeof(double), cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(h->d_in + c.offKb, hc.src[3], nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(h->d_in + c.offB, hc.src[4], nz * nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(h->d_in + c.offTc, hc.src[5], nz * nkb * sizeof(double), cudaMemcpyHostToDevice, cs));
+  for (size_t b = b0; b < b1; b++) {
+    int rc = upload_big(h, h->cos[b]);
+    if (rc) return rc;
   }
   return RTRG_OK;
 }
@@ -684,11 +687,17 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   }
   CU(cudaSetDevice(h->cfg.device));
   const size_t first = h->cos.size();
+  // layout: the small tables of this call form one slice (mirrored in the arena), the big raw
+  // tables of the direct cosmologies follow it
   size_t off = h->d_in_used, soff = h->stage.used;
   for (int i = 0; i < n; i++) {
     h->cos.push_back(describe_cosmology(list[i], off, soff));
-    off += h->cos.back().dev_len;
+    off += h->cos.back().stage_len;
     soff += h->cos.back().stage_len;
+  }
+  for (int i = 0; i < n; i++) {
+    place_big(h->cos[first + i], off);
+    off += h->cos[first + i].big_len;
   }
   if (soff > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
   if (h->stage.reserve(soff) != RTRG_OK) {
@@ -697,7 +706,6 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   }
   h->stage.used = soff;
   h->d_in_used = off;
-  bool resend_prefix = false;
   if (h->d_in_used > h->d_in_cap) {
     CU(cudaStreamSynchronize(h->copy_stream));
     double *q = nullptr;
@@ -707,16 +715,13 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     if (h->d_in) cudaFree(h->d_in);
     h->d_in = q;
     h->d_in_cap = ncap;
-    resend_prefix = first > 0;
+    int rc = upload_range(h, 0, first);  // the pool moved: what was sent before goes out again
+    if (rc) return rc;
   }
-  if (resend_prefix)
-    for (size_t b = 0; b < first; b++) {
-      int rc = upload_cosmology(h, h->cos[b]);
-      if (rc) return rc;
-    }
   // Staging runs on several host threads (the copies are memory-bound, one thread moves only
   // ~10 GB/s); every chunk is sent as soon as it is staged, so the PCIe transfer overlaps the
-  // staging of the next chunk.  Page-locked caller buffers skip the staging altogether.
+  // staging of the next chunk.  The big tables of page-locked cosmologies are not touched by
+  // the host at all: the copy engine reads them from the caller's buffers.
   int nth = host_threads(16);
   nth = std::max(1, std::min(nth, n));
   double *base = h->stage.base;
@@ -733,23 +738,8 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
         });
       for (auto &t : th) t.join();
     }
-    // consecutive staged cosmologies are contiguous in the arena and in the pool: one copy
-    int i = c0;
-    while (i < c1) {
-      const HostCosmo &hc = h->cos[first + i];
-      if (hc.direct) {
-        int rc = upload_cosmology(h, hc);
-        if (rc) return rc;
-        i++;
-        continue;
-      }
-      int j = i;
-      size_t len = 0;
-      while (j < c1 && !h->cos[first + j].direct) len += h->cos[first + j++].stage_len;
-      CU(cudaMemcpyAsync(h->d_in + hc.c.offT, base + hc.stage_off, len * sizeof(double), cudaMemcpyHostToDevice,
-                         h->copy_stream));
-      i = j;
-    }
+    int rc = upload_range(h, first + c0, first + c1);
+    if (rc) return rc;
   }
   h->prepared = h->uploaded = false;
   return RTRG_OK;
@@ -905,11 +895,10 @@ int rtrg_prepare(rtrg_handle *h) {
   CU(cudaMemsetAsync(h->work.base, 0, h->work.used, st));
   // --- input pool: rtrg_add_cosmologies already sent the staged tables on the copy stream.  A
   // repeated rtrg_prepare (the log transform below consumed the raw columns) sends them again.
-  if (h->d_in_transformed)
-    for (const HostCosmo &hc : h->cos) {
-      int rc = upload_cosmology(h, hc);
-      if (rc) return rc;
-    }
+  if (h->d_in_transformed) {
+    int rc = upload_range(h, 0, h->cos.size());
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(h->copy_done, h->copy_stream));
   CU(cudaStreamWaitEvent(st, h->copy_done, 0));
   h->d_in_transformed = true;
