@@ -922,7 +922,6 @@ int rtrg_device_init(rtrg_handle *h) {
   if (!h->uploaded) return fail(RTRG_EINVAL, "rtrg_prepare() has not uploaded any cosmology");
   CU(cudaSetDevice(h->cfg.device));
   h->prepared = false;
-  const rtrg_config &cfg = h->cfg;
   Batch &S = h->S;
   const IntegralTabs &tb = h->tb;
   const int B = S.B, nk = S.nk;

@@ -508,8 +508,6 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------- launchers
 enum { BIL_TPB = 352, BIL_PACK_MIN_B = 6 };  // batches of >= 6 cosmologies use the packed kernel
-// kernel variant (tuning knob, RTRG_BIL_VARIANT): 0 = 2 CTAs/SM (default); 1 = 1 CTA/SM
-static int g_bil_variant = 0;
 
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
   return (size_t)(3 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
@@ -521,10 +519,7 @@ static void launch_bilinear_class(const IntegralTabs &tb, const Batch &S, const 
   if (nitems == 0) return;
   dim3 g((nrows / BIL_R) * tb.nchunk, nitems, S.B);
   const size_t smem = bilinear_smem_bytes(tb);
-  if (NCD == 3 && g_bil_variant == 1)
-    k_bilinear<BIL_R, BIL_TPB, 1, 8, 3><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
-  else
-    k_bilinear<BIL_R, BIL_TPB, 2, 8, NCD><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
+  k_bilinear<BIL_R, BIL_TPB, 2, 8, NCD><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
 }
 
 // Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
@@ -564,7 +559,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     launches++;
   }
   RT_TIC(prof, PC_BILINEAR, st);
-  if (B >= BIL_PACK_MIN_B && g_bil_variant != 1) {
+  if (B >= BIL_PACK_MIN_B) {
     // batch: three (cosmology, spectrum) slots per CTA
     k_compact<<<1, 32, 0, st>>>(mask, B, S.act, S.nact);
     launches++;
@@ -616,11 +611,8 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 }
 
 int integrals_configure() {
-  const char *v = getenv("RTRG_BIL_VARIANT");
-  g_bil_variant = (v && *v) ? atoi(v) : 0;
   // opt in to the dynamic shared memory the bilinear kernel may need for large grids
   const int sm = 96 * 1024;
-  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 1, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(k_bilinear_packed<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);

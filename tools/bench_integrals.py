@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Micro-benchmark of the integral kernels: B cosmologies, `reps` evaluations per output-group
-mix.  usage: bench_integrals.py [B] [reps] [nk]   (kernel variant via RTRG_BIL_VARIANT)"""
+mix.  usage: bench_integrals.py [B] [reps] [nk]"""
 import os
 import sys
 
@@ -19,7 +19,7 @@ h.prepare()
 g = rt.grid_info(nk)
 peak = rt.dfma_peak_tflops(0, 0.3)
 flop_set = nk * (2.0 * g["nsup"] ** 2 + 6.0 * g["nsup"])
-print("variant=%s B=%d nk=%d  measured DFMA peak %.2f TFLOP/s" % (os.environ.get("RTRG_BIL_VARIANT", "0"), B, nk, peak))
+print("B=%d nk=%d  measured DFMA peak %.2f TFLOP/s" % (B, nk, peak))
 row, src, idx, kpw, cf = rt.assembly_terms()
 
 
