@@ -785,13 +785,29 @@ int rtrg_prepare(rtrg_handle *h) {
       aout[(size_t)b * MAX_OUT + i] = a;
       etaout[(size_t)b * MAX_OUT + i] = std::log(a / c.a_in);
     }
+    // The reference abort()s on look-ups outside its tables: D_dD needs 1e-3 <= a <= 1.1
+    // (hdr:644-649) at z_in, z1l and every output, Beta_P needs a <= 1.001 (hdr:528-531).  Such a
+    // cosmology is flagged and left out of the run; the rest of the batch is unaffected.
+    {
+      bool ok = c.a_in >= GROWTH_A_MIN && c.a_in <= GROWTH_A_MAX;
+      if (c.sw_nl && c.sw_1l) ok = ok && (1.0 / (1.0 + cfg.z1l) >= GROWTH_A_MIN);
+      for (int i = 0; i < c.n_out; i++) {
+        const double a = 1.0 / (1.0 + hc.z_out[i]);
+        ok = ok && a >= c.a_in && a <= (c.n_z > 0 && c.fnu >= 1e-10 ? 1.001 : GROWTH_A_MAX);
+        if (i > 0) ok = ok && hc.z_out[i] <= hc.z_out[i - 1];  // greatest to least (hdr:274)
+      }
+      if (!ok) cs[b].status = RTRG_RANGE_FAIL;
+    }
     h->ncols[b] = num_columns(cfg, c);
     h->out_off[b] = (long long)off;
     off += (size_t)c.n_out * nk * h->ncols[b];
     if (c.sw_nl && !c.sw_1l) h->any_full = true;
     if (c.sw_nl && c.sw_1l) h->any_1loop = true;
     if (c.sw_pr) h->any_pr = true;
+    const int st_keep = cs[b].status;
     cs[b] = c;
+    cs[b].status = st_keep;
+    h->cos[b].c.status = st_keep;
   }
   h->out_total = off;
   S.n_zmax = n_zmax;
@@ -967,9 +983,15 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   CU(cudaMemsetAsync(S.t, 0, B * sizeof(double), st));
   CU(cudaMemcpyAsync(S.h, h0.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(S.i_out, 0, B * sizeof(int), st));
-  CU(cudaMemsetAsync(S.done, 0, B * sizeof(int), st));
+  std::vector<int> done0(B);
+  int n_active = 0;
+  for (int b = 0; b < B; b++) {
+    done0[b] = h->cos[b].c.status != 0;  // flagged by rtrg_prepare / the device-side initialisation
+    n_active += !done0[b];
+  }
+  CU(cudaMemcpyAsync(S.done, done0.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(S.counters, 0, 4 * B * sizeof(long long), st));
-  CU(cudaMemcpyAsync(S.n_active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.n_active, &n_active, sizeof(int), cudaMemcpyHostToDevice, st));
 
   // --- k-sharded mode: all-gather of the ranks' ln P rows, max-reduction of the error norm
   const bool sharded = h->cfg.k_shards > 1;
@@ -998,7 +1020,6 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   }
   ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st));
 
-  int n_active = B;
   long long rounds = 0;
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
   while (n_active > 0 && rounds < max_rounds) {

@@ -177,3 +177,23 @@ def test_page_locked_inputs_take_the_direct_path(example1_dir):
     again, *_ = h.run()
     assert np.array_equal(again[1], tables[0]) and np.array_equal(again[2], tables[0])
     h.close()
+
+
+def test_out_of_range_cosmology_is_flagged_not_fatal(example1_dir):
+    """Where the reference abort()s (D_dD for a < 1e-3: z_in = 1500; Beta_P for a > 1.001:
+    z_out = -0.01) the cosmology gets a status word and the rest of the batch is untouched."""
+    good = rt.read_run_dir(example1_dir)
+    single, *_ = run(example1_dir)
+    bad1 = dict(good, z_in=1500.0)
+    bad2 = dict(good, z_out=np.array([1.0, -0.01]))
+    h = rt.RedTimeB200()
+    h.add_cosmologies([good, bad1, good, bad2])
+    h.prepare()
+    with pytest.raises(rt.RtrgError) as e:
+        h.run()
+    assert e.value.code == -5
+    tables, hdr, hdr0, status = h.run(raise_on_ode_failure=False)
+    assert list(status) == [0, 103, 0, 103]
+    assert np.array_equal(tables[0], single) and np.array_equal(tables[2], single)
+    assert not tables[1].any() and not tables[3].any()
+    h.close()
