@@ -35,7 +35,6 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cosmology*redshift outputs/sec at nk=128"
 UNIT = "outputs/s"
-NK = 128
 
 
 def parse_args():
@@ -48,6 +47,7 @@ def parse_args():
     ap.add_argument("--mode", default="1loop", choices=["1loop", "full"],
                     help="1loop = switches 1 1 1 1 (headline); full = 1 0 1 1 (full Time-RG)")
     ap.add_argument("--subsample", type=int, default=1, help="keep every n-th CAMB table row")
+    ap.add_argument("--nk", type=int, default=128, help="output wavenumbers (the headline metric is nk=128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--pageable", action="store_true",
@@ -64,8 +64,12 @@ def parse_args():
 def workload_name(a):
     sw = "1 1 1 1 (1-loop)" if a.mode == "1loop" else "1 0 1 1 (full Time-RG)"
     return ("throughput sweep (BASELINE configs[4]): %d w0wa+massive-nu cosmologies per GPU x 8 redshifts, "
-            "nk=128, switches %s, example-1 CAMB tables (%d rows x 12 redshifts) with per-cosmology tilt, "
-            "Latin-hypercube parameters seed 20261018" % (a.cosmologies, sw, -(-15447 // a.subsample)))
+            "nk=%d, switches %s, example-1 CAMB tables (%d rows x 12 redshifts) with per-cosmology tilt, "
+            "Latin-hypercube parameters seed 20261018" % (a.cosmologies, a.nk, sw, -(-15447 // a.subsample)))
+
+
+def metric_name(a):
+    return METRIC if a.nk == 128 else METRIC.replace("nk=128", "nk=%d" % a.nk)
 
 
 # ------------------------------------------------------------------------------------------
@@ -78,8 +82,12 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_binary():
-    p = os.path.join(ROOT, "oracle", "_ref", "redTime")
+def reference_binary(nk=128):
+    """The reference executable: nk is a compile-time constant there (redTime.cc:93)."""
+    name = {128: "redTime", 256: "redTime_nk256"}.get(nk)
+    if name is None:
+        return None
+    p = os.path.join(ROOT, "oracle", "_ref", name)
     return p if os.path.exists(p) else None
 
 
@@ -121,7 +129,7 @@ def run_reference_arm(a, rank):
         return
     steps = a.steps if a.steps is not None else 2
     warm = a.warmup if a.warmup is not None else 1
-    binary = reference_binary()
+    binary = reference_binary(a.nk)
     if binary is None:
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/redTime not built (make -C oracle)"}))
         return
@@ -135,7 +143,7 @@ def run_reference_arm(a, rank):
     wall = float(np.sum(t))
     value = steps * nproc * n_out / wall
     sample = "%d cosmologies x %d redshifts per step, one single-thread process per core" % (nproc, n_out)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+    line = {"impl": "reference", "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "sample": sample},
@@ -152,7 +160,7 @@ def REDSHIFTS():
 
 def cpu_baseline(a):
     """Bounded sample for the default bench line: ONE step of the reference arm."""
-    binary = reference_binary()
+    binary = reference_binary(a.nk)
     if binary is None:
         return None
     nproc = host_cores()
@@ -246,7 +254,7 @@ def run_b200(a, rank, world, local_rank):
     n_out = len(wl.REDSHIFTS_CE)
     outputs_per_step = B * n_out
 
-    h = rt.RedTimeB200(device=local_rank, nk=NK)
+    h = rt.RedTimeB200(device=local_rank, nk=a.nk)
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -326,7 +334,7 @@ def run_b200(a, rank, world, local_rank):
         # double-buffered: a second handle stages and uploads batch i+1 (host threads + copy
         # engine) while batch i is computed and read back -- every step still moves its own
         # inputs host->device and its own tables device->host inside the timed region
-        h2 = rt.RedTimeB200(device=local_rank, nk=NK)
+        h2 = rt.RedTimeB200(device=local_rank, nk=a.nk)
         hs = [h, h2]
         for hh in hs:                      # warm both handles' arenas
             hh.clear()
@@ -372,9 +380,9 @@ def run_b200(a, rank, world, local_rank):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel
-    grid = rt.grid_info(NK)
+    grid = rt.grid_info(a.nk)
     n_bil, ms_bil = prof["k_bilinear"]
-    flop_set = flops_per_matvec_set(grid, NK)
+    flop_set = flops_per_matvec_set(grid, a.nk)
     flop_total = flop_set * sets * steps
     peak = rt.dfma_peak_tflops(local_rank, 0.5)
     achieved = flop_total / (ms_bil * 1e-3) * 1e-12 if ms_bil > 0 else 0.0
@@ -389,10 +397,10 @@ def run_b200(a, rank, world, local_rank):
             "share_of_step": ms_bil / ms_total}
     kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in prof.items() if v[0]}
     cpu = None if a.no_cpu_baseline else cpu_baseline(a)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+    line = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "cosmologies_per_gpu": B, "redshifts": n_out, "nk": NK,
+            "config": {"workload": workload_name(a), "cosmologies_per_gpu": B, "redshifts": n_out, "nk": a.nk,
                        "mode": a.mode, "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2"
                        % (sum(c["Tc_b"].nbytes * 2 for c in cosmos) / 1e9)},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
