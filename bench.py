@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--nk", type=int, default=128, help="output wavenumbers (the headline metric is nk=128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full-beta", action="store_true",
+                    help="upload the full Beta_P(a,k) tables (default: the host pre-reduces them to what the run "
+                         "consumes, rtrg_config.reduce_beta = 1)")
     ap.add_argument("--pageable", action="store_true",
                     help="keep the synthetic input tables in pageable host memory (the library then stages "
                          "them through its own page-locked arena); default: page-locked inputs, direct H2D")
@@ -254,7 +257,8 @@ def run_b200(a, rank, world, local_rank):
     n_out = len(wl.REDSHIFTS_CE)
     outputs_per_step = B * n_out
 
-    h = rt.RedTimeB200(device=local_rank, nk=a.nk)
+    reduce_beta = 0 if a.full_beta else 1
+    h = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta)
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -325,8 +329,11 @@ def run_b200(a, rank, world, local_rank):
             tables, hdr, hdr0, status = e2e_step()
         torch.cuda.synchronize()
         t_serial = reduce_max(time.perf_counter() - t0)
-        h2d = sum(c["k_T"].nbytes * 3 + c["k_b"].nbytes + c["Tc_b"].nbytes * (1 if a.pageable else 2) +
-                  c["z_interp"].nbytes for c in cosmos)
+        if reduce_beta:   # k_T, Tc_T, Tb_T, a, k_b, beta(a=1,k_b), beta[n_z][nk + n_lnk + 1]
+            h2d = sum(c["k_T"].nbytes * 3 + c["k_b"].nbytes * 2 + c["z_interp"].nbytes * (1 + a.nk + 51) for c in cosmos)
+        else:
+            h2d = sum(c["k_T"].nbytes * 3 + c["k_b"].nbytes + c["Tc_b"].nbytes * (1 if a.pageable else 2) +
+                      c["z_interp"].nbytes for c in cosmos)
         h2d += B * (400 + 64 * 8 * 3)  # per-cosmology scalars and output redshift lists
         d2h = sum(t.nbytes for t in tables) + hdr.nbytes + hdr0.nbytes
         tables = [t.copy() for t in tables[B // 2:B // 2 + 1]] * B  # keep one table to compare against
@@ -339,7 +346,7 @@ def run_b200(a, rank, world, local_rank):
         # outputs/s), so multi-rank runs report the serial number.
         t_pipe = None
         if world == 1:
-            h2 = rt.RedTimeB200(device=local_rank, nk=a.nk)
+            h2 = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta)
             hs = [h, h2]
             for hh in hs:                      # warm both handles' arenas
                 hh.clear()
@@ -376,8 +383,9 @@ def run_b200(a, rank, world, local_rank):
                "double_buffered_value": None if t_pipe is None else world * outputs_per_step * steps / t_pipe,
                "serial_value": world * outputs_per_step * steps / t_serial, "serial_ms_per_step": 1e3 * t_serial / steps,
                "timing": "wall clock around the C-ABI calls, max over ranks",
-               "inputs": "pageable numpy buffers, staged by the library" if a.pageable else
-                         "page-locked numpy buffers (torch pin_memory), sent to the device directly",
+               "inputs": ("pageable" if a.pageable else "page-locked (torch pin_memory)") + " numpy buffers holding the "
+                         "full CAMB tables; " + ("the host pre-reduces the Beta_P table to what the run consumes "
+                                                 "(reduce_beta=1)" if reduce_beta else "full Beta_P tables uploaded"),
                "path": "per step: rtrg_add_cosmologies (page-locked caller buffers: asynchronous H2D straight from "
                        "them; pageable ones: copied to a page-locked arena on host threads, chunked H2D overlapped) "
                        "-> rtrg_prepare -> rtrg_run -> "

@@ -141,6 +141,7 @@ struct rtrg_handle {
   double *d_T0 = nullptr;
   double *d_kgrid = nullptr;
   std::vector<double> kgrid;
+  std::vector<double> slot_k;  // reduce_beta: clamped wavenumbers of the nkk pre-reduced beta columns
   std::vector<HostCosmo> cos;
   Batch S;
   bool prepared = false, uploaded = false;
@@ -423,6 +424,14 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     lnkArr[i] = lnkmin + g.dlnk * i;
     h->kgrid[i] = std::exp(lnkArr[i]);
   }
+  // wavenumbers of the pre-reduced beta columns: the nk grid values, then the growth-table ones,
+  // clamped as Beta_P does (hdr:538-545)
+  {
+    const double lnk_min = std::log(GROWTH_K_MIN), dl = std::log(GROWTH_K_MAX / GROWTH_K_MIN) / cfg->n_lnk;
+    for (int i = 0; i < nk; i++) h->slot_k.push_back(h->kgrid[i]);
+    for (int j = 0; j <= cfg->n_lnk; j++) h->slot_k.push_back(std::exp(lnk_min + dl * j));
+    for (double &k : h->slot_k) k = std::min(std::max(k, cfg->beta_kmin), cfg->beta_kmax);
+  }
   // --- Pab stencil for every padded sample (rt:181-232, itp:68-78)
   std::vector<int> ex_n0(np);
   std::vector<double> ex_w((size_t)4 * np, 0.0), ex_dx(np, 0.0);
@@ -596,7 +605,7 @@ static bool is_page_locked(const void *p) {
 // when it is formed on the host) start at device-pool offset `off` = staging-arena offset `soff`
 // region; the two big raw tables of a direct cosmology (T_nu, T_c of the interpolation files)
 // are placed by the caller afterwards (place_big).
-static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off, size_t soff) {
+static HostCosmo describe_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, size_t off, size_t soff) {
   HostCosmo hc;
   Cosmo &c = hc.c;
   std::memset(&c, 0, sizeof c);
@@ -618,8 +627,17 @@ static HostCosmo describe_cosmology(const rtrg_cosmology *in, size_t off, size_t
   c.offKb = (long long)(off + 3 * nT + nz);
   c.offB = (long long)(off + 3 * nT + nz + nkb);
   c.offTc = -1;
-  hc.direct = nz > 0 && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b);
+  c.offRow1 = c.offBred = -1;
   hc.stage_off = soff;
+  if (h->cfg.reduce_beta && nz > 0) {
+    // only what the run consumes: beta(a=1, k_b) and beta at the nkk slot wavenumbers
+    const size_t nkk = h->slot_k.size();
+    c.offRow1 = c.offB;
+    c.offBred = c.offB + (long long)nkb;
+    hc.stage_len = 3 * nT + nz + nkb + nkb + nz * nkk;
+    return hc;
+  }
+  hc.direct = nz > 0 && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b);
   hc.stage_len = 3 * nT + nz + nkb + (hc.direct ? 0 : nz * nkb);
   hc.big_len = hc.direct ? 2 * nz * nkb : 0;
   if (hc.direct) hc.src[0] = in->Tnu_b, hc.src[1] = in->Tc_b;
@@ -632,7 +650,7 @@ static void place_big(HostCosmo &hc, size_t off_big) {
 }
 // copy the caller's small tables into the staging arena; pageable interpolation tables are
 // reduced to beta = f_nu T_nu / T_c on the way (hdr:556-623), which halves their PCIe bytes
-static void stage_cosmology(const rtrg_cosmology *in, const HostCosmo &hc, double *base) {
+static void stage_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, const HostCosmo &hc, double *base) {
   const Cosmo &c = hc.c;
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
   double *s = base + hc.stage_off;
@@ -641,6 +659,33 @@ static void stage_cosmology(const rtrg_cosmology *in, const HostCosmo &hc, doubl
   std::memcpy(s + 2 * nT, in->Tb_T, nT * sizeof(double));
   for (size_t i = 0; i < nz; i++) s[3 * nT + i] = 1.0 / (1.0 + in->z_interp[i]);
   if (nz) std::memcpy(s + 3 * nT + nz, in->k_b, nkb * sizeof(double));
+  if (nz && c.offRow1 >= 0) {
+    // pre-reduction of the beta table: the 2-D rule interpolates in a first, column
+    // by column, and then in k (tab:262-328), so (i) the row at a = 1 and (ii) the k-stencil
+    // applied to every a row are all the run needs.  Same arithmetic as beta_P / k_beta_reduce.
+    const double fn = c.On / c.Om;
+    const double *tn = in->Tnu_b, *tc = in->Tc_b, *a = s + 3 * nT, *kb = in->k_b;
+    auto beta = [&](size_t j, size_t i) { return fn * tn[j * nkb + i] / tc[j * nkb + i]; };
+    double *row1 = s + 3 * nT + nz + nkb, *bred = row1 + nkb;
+    const int X = (int)nz, nx = tab_find(a, X, 1.0);
+    for (size_t i = 0; i < nkb; i++) {
+      if (nx > 0 && nx < X - 2)
+        row1[i] = cub4(a + nx - 1, beta(nx - 1, i), beta(nx, i), beta(nx + 1, i), beta(nx + 2, i), 1.0);
+      else
+        row1[i] = lin2(a[nx], a[nx + 1], beta(nx, i), beta(nx + 1, i), 1.0);
+    }
+    const size_t nkk = h->slot_k.size();
+    for (size_t kk = 0; kk < nkk; kk++) {
+      const Stencil st = tab_stencil_y(kb, (int)nkb, h->slot_k[kk]);
+      for (size_t j = 0; j < nz; j++) {
+        double r = 0;
+        for (int m = 0; m < 4; m++)
+          if (st.w[m] != 0.0) r += st.w[m] * beta(j, (size_t)(st.n0 + m));
+        bred[j * nkk + kk] = r;
+      }
+    }
+    return;
+  }
   if (nz && !hc.direct) {
     const double fn = c.On / c.Om;
     const double *tn = in->Tnu_b, *tc = in->Tc_b;
@@ -691,7 +736,7 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   // tables of the direct cosmologies follow it
   size_t off = h->d_in_used, soff = h->stage.used;
   for (int i = 0; i < n; i++) {
-    h->cos.push_back(describe_cosmology(list[i], off, soff));
+    h->cos.push_back(describe_cosmology(h, list[i], off, soff));
     off += h->cos.back().stage_len;
     soff += h->cos.back().stage_len;
   }
@@ -729,12 +774,12 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int c1 = std::min(n, c0 + chunk);
     if (nth == 1) {
-      for (int i = c0; i < c1; i++) stage_cosmology(list[i], h->cos[first + i], base);
+      for (int i = c0; i < c1; i++) stage_cosmology(h, list[i], h->cos[first + i], base);
     } else {
       std::vector<std::thread> th;
       for (int t = 0; t < nth; t++)
         th.emplace_back([=]() {
-          for (int i = c0 + t; i < c1; i += nth) stage_cosmology(list[i], h->cos[first + i], base);
+          for (int i = c0 + t; i < c1; i += nth) stage_cosmology(h, list[i], h->cos[first + i], base);
         });
       for (auto &t : th) t.join();
     }

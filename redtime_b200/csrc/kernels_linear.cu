@@ -81,6 +81,11 @@ __global__ void k_beta_reduce(Batch S, const double *__restrict__ kgrid) {
     for (int j = 0; j < S.n_zmax; j++) out[(long long)j * S.nkk] = 0.0;
     return;
   }
+  if (c.offRow1 >= 0) {  // reduced upload: the host already applied the k stencils
+    for (int j = 0; j < c.n_z; j++) out[(long long)j * S.nkk] = S.in[c.offBred + (long long)j * S.nkk + kk];
+    for (int j = c.n_z; j < S.n_zmax; j++) out[(long long)j * S.nkk] = 0.0;
+    return;
+  }
   double k = slot_k(S, kgrid, kk);
   if (k < S.beta_kmin) k = S.beta_kmin;  // hdr:538-545
   if (k > S.beta_kmax) k = S.beta_kmax;

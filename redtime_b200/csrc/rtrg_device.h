@@ -146,7 +146,8 @@ RT_HD BetaTab beta_tab(const Batch &S, const Cosmo &c) {
   t.n_kb = c.n_kb;
   t.a = S.in + c.offA;
   t.k = S.in + c.offKb;
-  t.beta = S.in + c.offB;
+  t.beta = c.offRow1 >= 0 ? nullptr : S.in + c.offB;
+  t.row1 = c.offRow1 >= 0 ? S.in + c.offRow1 : nullptr;
   t.fn = c.On / c.Om;
   t.kmin = S.beta_kmin;
   t.kmax = S.beta_kmax;

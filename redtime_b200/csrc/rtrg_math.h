@@ -45,6 +45,9 @@ struct Cosmo {
   long long offB;     // beta = f_nu T_nu / T_c [n_z][n_kb]  (hdr:556-623): formed while staging, or
                       // (page-locked caller buffers, sent as they are) T_nu here until
   long long offTc;    // k_prep_inputs divides by the raw T_c stored at offTc; -1 when staged
+  // reduce_beta: instead of the full beta table the host sends what the run consumes:
+  long long offRow1;  // beta(a = 1, k_b[*]) [n_kb] (sigma_8 / sigma_v integrands); -1: full table
+  long long offBred;  // beta pre-reduced in k at the nk grid and n_lnk+1 growth wavenumbers [n_z][nkk]
   // results of the device-side initialisation
   double Norm;        // sigma_8 normalisation (hdr:874)
   double sigv2_0;     // sigma_v^2(z=0)       (hdr:961)
@@ -230,7 +233,8 @@ struct BetaTab {
   int n_z, n_kb;
   const double *a;     // [n_z] ascending
   const double *k;     // [n_kb]
-  const double *beta;  // [n_z][n_kb]  (k fastest, as tab: f[ny + Y*nx])
+  const double *beta;  // [n_z][n_kb]  (k fastest, as tab: f[ny + Y*nx]); nullptr when reduced
+  const double *row1;  // reduced upload: the table interpolated in a at a = 1, [n_kb]
   double fn, kmin, kmax;
 };
 // returns NaN for a > 1.001 (the reference aborts, hdr:528-531)
@@ -241,6 +245,14 @@ RT_HD double beta_P(const BetaTab &t, double a, double k) {
   if (a > 1.0) a = 1.0;
   if (k < t.kmin) k = t.kmin;
   if (k > t.kmax) k = t.kmax;
+  if (!t.beta) {
+    // reduced upload: only a = 1 is available in general k (tab2d interpolates in a first, column
+    // by column, so the pre-interpolated row followed by the k rule gives the same value)
+    if (a != 1.0) return NAN;
+    const int ny = tab_find(t.k, t.n_kb, k);
+    if (ny > 0 && ny < t.n_kb - 2) return cub4(t.k + ny - 1, t.row1[ny - 1], t.row1[ny], t.row1[ny + 1], t.row1[ny + 2], k);
+    return lin2(t.k[ny], t.k[ny + 1], t.row1[ny], t.row1[ny + 1], k);
+  }
   return tab2d(t.a, t.n_z, t.k, t.n_kb, t.beta, a, k);
 }
 // the same look-up through a row pre-reduced in k: brow[j] = sum_r wy_r beta[j][ny-1+r]

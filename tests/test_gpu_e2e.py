@@ -197,3 +197,28 @@ def test_out_of_range_cosmology_is_flagged_not_fatal(example1_dir):
     assert np.array_equal(tables[0], single) and np.array_equal(tables[2], single)
     assert not tables[1].any() and not tables[3].any()
     h.close()
+
+
+def test_reduced_beta_upload(example1_dir, example1_full_dir):
+    """reduce_beta = 1: the host sends beta(a=1,k) and the table pre-reduced in k instead of the
+    full Beta_P(a,k) table.  Same interpolation rules in the other order: results
+    agree to round-off (host code has no FMA contraction, the device code has)."""
+    for d in (example1_dir, example1_full_dir):
+        full, hdr_f, hdr0_f, _, cnt_f = run(d)
+        red, hdr_r, hdr0_r, _, cnt_r = run(d, reduce_beta=1)
+        assert cnt_f == cnt_r
+        assert np.max(np.abs(red[:, :, :10] - full[:, :, :10]) / np.abs(full[:, :, :10]).clip(1e-300)) < 1e-12
+        assert np.max(np.abs(red - full) / (np.abs(full) + 1e-12 * np.abs(full).max(axis=1, keepdims=True) + 1e-300)) < 1e-9
+        assert np.max(np.abs(hdr_r[:7] / hdr_f[:7] - 1)) < 1e-13 and np.max(np.abs(hdr0_r / hdr0_f - 1)) < 1e-13
+    h = rt.RedTimeB200(reduce_beta=1)
+    h.add_cosmology(rt.read_run_dir(example1_dir))
+    h.prepare()
+    k = np.array([1e-3, 0.05, 1.0, 3.0])
+    ref = rt.RedTimeB200()
+    ref.add_cosmology(rt.read_run_dir(example1_dir))
+    ref.prepare()
+    assert np.max(np.abs(h.Beta_P(1.0, k) / ref.Beta_P(1.0, k) - 1)) < 1e-14
+    with pytest.raises(rt.RtrgError):
+        h.Beta_P(0.5, k)   # only a = 1 was uploaded
+    h.close()
+    ref.close()
