@@ -212,7 +212,7 @@ def test_reduced_beta_upload(example1_dir, example1_full_dir):
         # H2/V9: the reference's own round-off floor); compare them above k = 5.7e-3 h/Mpc
         hi = full[0, :, 0] > 5.7e-3
         assert np.max(np.abs(red[:, hi] - full[:, hi]) / (np.abs(full[:, hi]) + 1e-300)) < 1e-8
-        assert np.max(np.abs(hdr_r[:7] / hdr_f[:7] - 1)) < 1e-13 and np.max(np.abs(hdr0_r / hdr0_f - 1)) < 1e-13
+        assert np.allclose(hdr_r[:7], hdr_f[:7], rtol=1e-13, atol=0) and np.allclose(hdr0_r, hdr0_f, rtol=1e-13, atol=0)
     h = rt.RedTimeB200(reduce_beta=1)
     h.add_cosmology(rt.read_run_dir(example1_dir))
     h.prepare()
