@@ -96,15 +96,85 @@ __global__ void k_beta_reduce(Batch S, const double *__restrict__ kgrid) {
   for (int j = c.n_z; j < S.n_zmax; j++) out[(long long)j * S.nkk] = 0.0;
 }
 
+// Right-hand side of the growth ODE as the device integrates it: the arithmetic of growth_rhs
+// (rtrg_math.h) with the a-direction look-up of beta made cheap -- the a nodes and the reciprocal
+// Lagrange denominators of every interval sit in shared memory (one block = one cosmology), the
+// interval of the previous call is tried first, and E(a) is one exp of p ln a + q (1 - a).
+// Differences to growth_rhs are at the 1e-16 level per call (reciprocal products instead of
+// chained divisions); the step sequence GSL takes is unchanged.
+struct GrowthRhsDev {
+  BgStatic bg;
+  const double *brow;   // beta at this wavenumber for every a node, stride bstride
+  long long bstride;
+  const double *s_a;    // [n_z] a nodes (shared)
+  const double *s_inv;  // [n_z][4] reciprocal denominators of the cubic on nodes n-1..n+2 (shared)
+  int n_z;
+  bool has_beta;
+  mutable int n_last;
+  __device__ __forceinline__ double beta(double a) const {
+    if (!has_beta) return 0.0;
+    if (a > 1.0) a = 1.0;
+    int n = n_last;
+    const int X = n_z;
+    if (!((n == 0 || s_a[n] < a) && (s_a[n + 1] >= a || n == X - 2))) {
+      n = tab_find(s_a, X, a);
+      n_last = n;
+    }
+    if (n > 0 && n < X - 2) {
+      const double d0 = a - s_a[n - 1], d1 = a - s_a[n], d2 = a - s_a[n + 1], d3 = a - s_a[n + 2];
+      const double *iv = s_inv + 4 * n;
+      return d1 * d2 * d3 * iv[0] * brow[(n - 1) * bstride] + d0 * d2 * d3 * iv[1] * brow[n * bstride] +
+             d0 * d1 * d3 * iv[2] * brow[(n + 1) * bstride] + d0 * d1 * d2 * iv[3] * brow[(n + 2) * bstride];
+    }
+    const double f0 = brow[n * bstride], f1 = brow[(n + 1) * bstride];
+    return f0 + (f1 - f0) * iv_lin(n) * (a - s_a[n]);
+  }
+  __device__ __forceinline__ double iv_lin(int n) const { return 1.0 / (s_a[n + 1] - s_a[n]); }
+  __device__ __forceinline__ void operator()(double a, const double y[2], double f[2]) const {
+    const BgStatic &s = bg;
+    const double a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a4 * a, ainv = 1.0 / a;
+    const double E = exp(-3.0 * (1.0 + s.w0 + s.wa) * log(a) - 3.0 * s.wa * (1.0 - a));
+    const double dEda = 3.0 * E * (s.wa - (1.0 + s.w0 + s.wa) * ainv);
+    const double Y = bgs_Y(s, a), dYda = bgs_dYda(s, a);
+    const double H2 = (s.Om - s.On) * (1.0 + Y) / a3 + s.OL * E + s.Og / a4;
+    const double dlnH = 0.5 * a / H2 *
+                        (s.fc * s.Om * (-3.0 * (1.0 + Y) + a * dYda) / a4 + s.OL * dEda - 4.0 * s.Og / a5);
+    const double F0 = 1.5 * s.Om / (a5 * H2);
+    const double F1 = (3.0 + dlnH) * ainv;
+    const double bt = (a < 1e-3) ? s.fn : beta(a);
+    f[0] = y[1];
+    f[1] = -F1 * y[1] + F0 * (s.fc + bt) * y[0];
+  }
+};
+
 __global__ void __launch_bounds__(64) k_growth_ode(Batch S) {
   const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > S.n_lnk) return;
   const Cosmo &c = S.cosmo[b];
-  GrowthCtx g;
+  extern __shared__ double s_g[];  // [n_z] a nodes, [n_z][4] reciprocal denominators
+  double *s_a = s_g, *s_inv = s_g + S.n_zmax;
+  const bool has_beta = c.n_z > 0 && c.On / c.Om >= 1e-10;
+  const double *an = S.in + c.offA;
+  for (int n = threadIdx.x; n < c.n_z; n += blockDim.x) {
+    s_a[n] = an[n];
+    if (n > 0 && n < c.n_z - 2) {
+      const double *p = an + n - 1;
+      s_inv[4 * n + 0] = 1.0 / ((p[0] - p[1]) * (p[0] - p[2]) * (p[0] - p[3]));
+      s_inv[4 * n + 1] = 1.0 / ((p[1] - p[0]) * (p[1] - p[2]) * (p[1] - p[3]));
+      s_inv[4 * n + 2] = 1.0 / ((p[2] - p[0]) * (p[2] - p[1]) * (p[2] - p[3]));
+      s_inv[4 * n + 3] = 1.0 / ((p[3] - p[0]) * (p[3] - p[1]) * (p[3] - p[2]));
+    }
+  }
+  __syncthreads();
+  if (j > S.n_lnk) return;
+  GrowthRhsDev g;
   g.bg = bg_static(c);
-  g.bt = beta_tab(S, c);
   g.brow = S.bred + (long long)b * S.n_zmax * S.nkk + (S.nk + j);
   g.bstride = S.nkk;
+  g.s_a = s_a;
+  g.s_inv = s_inv;
+  g.n_z = c.n_z;
+  g.has_beta = has_beta;
+  g.n_last = 0;
   const int nj = S.n_lnk + 1;
   double *G = S.G + (long long)b * (S.n_lna + 1) * nj, *dD = S.dD + (long long)b * (S.n_lna + 1) * nj;
   double y[2] = {1.0, 1.0 / S.a_early};  // hdr:697-698
@@ -311,7 +381,7 @@ int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Pro
   k_beta_reduce<<<dim3((S.nkk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
   RT_TOC(prof, st);
   RT_TIC(prof, PC_GROWTH_ODE, st);
-  k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;
+  k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, (size_t)5 * S.n_zmax * sizeof(double), st>>>(S), n++;
   RT_TOC(prof, st);
   RT_TIC(prof, PC_GROWTH_TABS, st);
   k_growth_norm<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;

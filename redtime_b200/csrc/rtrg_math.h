@@ -392,6 +392,7 @@ struct GrowthCtx {
   BetaTab bt;
   const double *brow;  // beta row pre-reduced at this wavenumber (clamped k)
   long long bstride;   // stride between successive a-nodes of brow
+  RT_HD void operator()(double a, const double y[2], double f[2]) const;
 };
 // One evaluation costs one pow + one exp (the dark-energy factor E, shared by H^2 and
 // dlnH/dlna) and a handful of multiplications: the integer powers of a are products, not
@@ -410,6 +411,8 @@ RT_HD void growth_rhs(const GrowthCtx &g, double a, const double y[2], double f[
   f[0] = y[1];
   f[1] = -F1 * y[1] + F0 * (s.fc + beta) * y[0];  // F_MG = 0 (hdr:151-153)
 }
+
+RT_HD void GrowthCtx::operator()(double a, const double y[2], double f[2]) const { growth_rhs(*this, a, y, f); }
 
 struct PDTableau {
   double A[13][12], C[13], B8[13], B7[13];
@@ -430,7 +433,8 @@ inline PDTableau make_pd_tableau() {
 }
 
 // one leg a_begin -> a_end (hdr:170-190); returns number of attempted steps
-RT_HD int growth_integrate(const PDTableau &PD, const GrowthCtx &g, double a_begin, double a_end,
+template <class Rhs>
+RT_HD int growth_integrate(const PDTableau &PD, const Rhs &g, double a_begin, double a_end,
                            double y[2]) {
   const double(*A)[12] = PD.A;
   const double *C = PD.C, *B8 = PD.B8, *B7 = PD.B7;
@@ -443,7 +447,7 @@ RT_HD int growth_integrate(const PDTableau &PD, const GrowthCtx &g, double a_beg
     const double t0 = t, dt = t1 - t0;
     const double y0[2] = {y[0], y[1]};
     double k[13][2];
-    growth_rhs(g, t0, y0, k[0]);
+    g(t0, y0, k[0]);
     double h0 = h;
     for (;;) {
       bool final_step = false;
@@ -461,7 +465,7 @@ RT_HD int growth_integrate(const PDTableau &PD, const GrowthCtx &g, double a_beg
           }
         }
         const double yt[2] = {y0[0] + h0 * acc0, y0[1] + h0 * acc1};
-        growth_rhs(g, t0 + C[s] * h0, yt, k[s]);
+        g(t0 + C[s] * h0, yt, k[s]);
       }
       double s8[2] = {0, 0}, s7[2] = {0, 0};
       for (int j = 0; j < 13; j++) {
