@@ -33,17 +33,45 @@ __device__ __forceinline__ bool ode_row_D_dD(const Batch &S, int b, int i, doubl
 
 // ---------------------------------------------------------------------------- k_rhs
 // stage < 0: eta = t[b]; otherwise eta = t[b] + c_stage * h_try[b].
+// Everything that depends on the time only (background, interpolation weights in a of the beta
+// and growth tables, powers of e^eta) is evaluated once per block and shared: the 128 rows of a
+// block belong to one cosmology and are evaluated at the same eta.  The rows then read their 41
+// state values, 38 sources and a few table entries: HBM traffic 960 B per row.
+struct RhsShared {
+  double eta, A, om10_den, Om11, z, a, pre4;
+  RowX xb, xg;
+  int beta_zero, beta_bad, growth_ok;
+};
 __global__ void __launch_bounds__(128)
     k_rhs(Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv,
           double *__restrict__ dyv, int stage, const int *__restrict__ mask) {
   const int b = blockIdx.y;
   if (mask && !mask[b]) return;
-  const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.k_hi) return;
   const Cosmo &c = S.cosmo[b];
   const int nk = S.nk;
-  const double eta = (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b];
-  const double A = c.a_in * exp(eta);  // rt:1430
+  __shared__ RhsShared sh;
+  if (threadIdx.x == 0) {
+    const double eta = (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b];
+    const double A = c.a_in * exp(eta);  // rt:1430
+    sh.eta = eta;
+    sh.A = A;
+    sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
+    sh.Om11 = 3.0 + bg_dlnH(c, A);
+    // Beta_P(A, k): 0 without massive neutrinos, abort in the reference for A > 1.001 (hdr:523-531)
+    sh.beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10);
+    sh.beta_bad = (!sh.beta_zero && A > 1.001);
+    if (!sh.beta_zero && !sh.beta_bad) sh.xb = tab_row_x_prepare(S.in + c.offA, c.n_z, A > 1.0 ? 1.0 : A);
+    // growth look-up of the 1-loop rescaling (rt:1316-1337)
+    sh.z = exp(-eta) * (1.0 + c.z_in) - 1;
+    sh.a = 1.0 / (sh.z + 1.0);
+    sh.growth_ok = !(sh.a > GROWTH_A_MAX || sh.a < GROWTH_A_MIN);
+    if (sh.growth_ok) sh.xg = tab_row_x_prepare(S.lna, S.n_lna + 1, log(sh.a));
+    sh.pre4 = exp(-4.0 * eta);
+  }
+  __syncthreads();
+  const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.k_hi) return;
+  const double eta = sh.eta;
   const double k = kgrid[i];
 
   double y[N_U], dy[N_U];
@@ -51,20 +79,27 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
   for (int j = 0; j < N_U; j++) y[j] = yb[(long long)j * nk];
 
-  double Om10, Om11;
-  trg_omega(c, A, ode_row_beta(S, b, i, A), &Om10, &Om11);
+  double beta = 0.0;
+  if (sh.beta_bad) beta = NAN;
+  else if (!sh.beta_zero) beta = tab_row_x_apply(sh.xb, S.bred + (long long)b * S.n_zmax * S.nkk + i, S.nkk);
+  const double Om10 = -1.5 * c.Om * (c.fcb + beta) / sh.om10_den, Om11 = sh.Om11;
 
   double A14[N_UI], R24[N_UQ];
   const int evolve_Q = (S.print_Q || c.sw_pr);
   if (c.sw_nl) {
     if (c.sw_1l) {
       // rescale the z1l cache (rt:1316-1337)
-      const double z = exp(-eta) * (1.0 + c.z_in) - 1;
-      double D = 0, dD = 0;
-      ode_row_D_dD(S, b, i, z, &D, &dD);
+      const double z = sh.z;
+      double D = NAN, dD = NAN;
+      if (sh.growth_ok) {
+        const long long o = (long long)b * (S.n_lna + 1) * nk + i;
+        const double D0 = S.D0row[(long long)b * nk + i];
+        D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
+        dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
+      }
       const double fz = dD / (D * (1.0 + z));
       const double rD = D / S.D_z1l[(long long)b * nk + i];
-      const double pre = (rD * rD) * (rD * rD) * exp(-4.0 * eta);
+      const double pre = (rD * rD) * (rD * rD) * sh.pre4;
       const double *s1 = S.src_z1l + (long long)b * N_SRC * nk + i;
       double fp[5];
       fp[0] = 1.0;

@@ -205,6 +205,37 @@ RT_HD double tab_row_x(const double *xs, int X, const double *g, double xq, long
     return cub4(xs + nx - 1, g[(nx - 1) * gs], g[nx * gs], g[(nx + 1) * gs], g[(nx + 2) * gs], xq);
   return lin2(xs[nx], xs[nx + 1], g[nx * gs], g[(nx + 1) * gs], xq);
 }
+// The same rule split in two: the part that depends on the abscissa only (shared by every row
+// that is looked up at the same xq) and its application to one row.  The weights are cub4's own
+// quotient chains, so apply() returns what tab_row_x returns.
+struct RowX {
+  int nx, cub;
+  double w[4];   // cubic: weights on nodes nx-1..nx+2
+  double x0, x1, xq;  // linear: the two nodes
+};
+RT_HD RowX tab_row_x_prepare(const double *xs, int X, double xq) {
+  RowX r;
+  r.nx = tab_find(xs, X, xq);
+  r.cub = (r.nx > 0 && r.nx < X - 2);
+  r.xq = xq;
+  r.x0 = xs[r.nx];
+  r.x1 = xs[r.nx + 1];
+  r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0;
+  if (r.cub) {
+    const double *x = xs + r.nx - 1;
+    r.w[0] = (xq - x[1]) * (xq - x[2]) * (xq - x[3]) / (x[0] - x[1]) / (x[0] - x[2]) / (x[0] - x[3]);
+    r.w[1] = (xq - x[0]) * (xq - x[2]) * (xq - x[3]) / (x[1] - x[0]) / (x[1] - x[2]) / (x[1] - x[3]);
+    r.w[2] = (xq - x[0]) * (xq - x[1]) * (xq - x[3]) / (x[2] - x[0]) / (x[2] - x[1]) / (x[2] - x[3]);
+    r.w[3] = (xq - x[0]) * (xq - x[1]) * (xq - x[2]) / (x[3] - x[0]) / (x[3] - x[1]) / (x[3] - x[2]);
+  }
+  return r;
+}
+RT_HD double tab_row_x_apply(const RowX &r, const double *g, long long gs = 1) {
+  if (r.cub)
+    return r.w[0] * g[(r.nx - 1) * gs] + r.w[1] * g[r.nx * gs] + r.w[2] * g[(r.nx + 1) * gs] +
+           r.w[3] * g[(r.nx + 2) * gs];
+  return lin2(r.x0, r.x1, g[r.nx * gs], g[(r.nx + 1) * gs], r.xq);
+}
 // y-direction weights of the 2-D table (rows ny-1..ny+2; linear at the two edge intervals)
 RT_HD Stencil tab_stencil_y(const double *ys, int Y, double yq) {
   Stencil s;
