@@ -71,57 +71,69 @@ __global__ void __launch_bounds__(128)
   __syncthreads();
   const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.k_hi) return;
-  const double eta = sh.eta;
+  const double eta = sh.eta, eeta = exp(eta);
   const double k = kgrid[i];
-
-  double y[N_U], dy[N_U];
-  const double *yb = yv + (long long)b * N_U * nk + i;
-#pragma unroll
-  for (int j = 0; j < N_U; j++) y[j] = yb[(long long)j * nk];
 
   double beta = 0.0;
   if (sh.beta_bad) beta = NAN;
   else if (!sh.beta_zero) beta = tab_row_x_apply(sh.xb, S.bred + (long long)b * S.n_zmax * S.nkk + i, S.nkk);
   const double Om10 = -1.5 * c.Om * (c.fcb + beta) / sh.om10_den, Om11 = sh.Om11;
 
-  double A14[N_UI], R24[N_UQ];
+  // 1-loop mode: the sources are the z1l cache rescaled by (D/D_z1l)^4 e^{-4 eta} f^n (rt:1316-1337)
+  const int one_loop = c.sw_nl && c.sw_1l;
   const int evolve_Q = (S.print_Q || c.sw_pr);
-  if (c.sw_nl) {
-    if (c.sw_1l) {
-      // rescale the z1l cache (rt:1316-1337)
-      const double z = sh.z;
-      double D = NAN, dD = NAN;
-      if (sh.growth_ok) {
-        const long long o = (long long)b * (S.n_lna + 1) * nk + i;
-        const double D0 = S.D0row[(long long)b * nk + i];
-        D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
-        dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
-      }
-      const double fz = dD / (D * (1.0 + z));
-      const double rD = D / S.D_z1l[(long long)b * nk + i];
-      const double pre = (rD * rD) * (rD * rD) * sh.pre4;
-      const double *s1 = S.src_z1l + (long long)b * N_SRC * nk + i;
-      double fp[5];
-      fp[0] = 1.0;
-#pragma unroll
-      for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
-#pragma unroll
-      for (int j = 0; j < N_UI; j++) A14[j] = pre * fp[a14_fpow(j)] * s1[(long long)j * nk];
-#pragma unroll
-      for (int j = 0; j < N_UQ; j++)
-        R24[j] = evolve_Q ? pre * fp[r24_fpow(j)] * s1[(long long)(N_UI + j) * nk] : 0.0;
-    } else {
-      const double *s1 = S.src + (long long)b * N_SRC * nk + i;
-#pragma unroll
-      for (int j = 0; j < N_UI; j++) A14[j] = s1[(long long)j * nk];
-#pragma unroll
-      for (int j = 0; j < N_UQ; j++) R24[j] = evolve_Q ? s1[(long long)(N_UI + j) * nk] : 0.0;
+  double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pre = 1.0;
+  if (one_loop) {
+    double D = NAN, dD = NAN;
+    if (sh.growth_ok) {
+      const long long o = (long long)b * (S.n_lna + 1) * nk + i;
+      const double D0 = S.D0row[(long long)b * nk + i];
+      D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
+      dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
     }
-  }
-  trg_rhs_row(eta, k, Om10, Om11, c.sw_nl, evolve_Q, y, A14, R24, dy);
-  double *db = dyv + (long long)b * N_U * nk + i;
+    const double fz = dD / (D * (1.0 + sh.z));
+    const double rD = D / S.D_z1l[(long long)b * nk + i];
+    pre = (rD * rD) * (rD * rD) * sh.pre4;
 #pragma unroll
-  for (int j = 0; j < N_U; j++) db[(long long)j * nk] = dy[j];
+    for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
+  }
+  const double *s1 = (one_loop ? S.src_z1l : S.src) + (long long)b * N_SRC * nk + i;
+  const double *yb = yv + (long long)b * N_U * nk + i;
+  double *db = dyv + (long long)b * N_U * nk + i;
+
+  // The row is processed in four pieces (ln P + I, then the three multipoles of Q) so that at
+  // most 17 + 14 + 17 values are live at a time: 4x the occupancy of holding all 41 + 38 + 41.
+  {
+    double y[N_UP + N_UI], dy[N_UP + N_UI], A14[N_UI];
+#pragma unroll
+    for (int j = 0; j < N_UP + N_UI; j++) y[j] = yb[(long long)j * nk];
+#pragma unroll
+    for (int j = 0; j < N_UI; j++)
+      A14[j] = !c.sw_nl ? 0.0 : one_loop ? pre * fp[a14_fpow(j)] * s1[(long long)j * nk] : s1[(long long)j * nk];
+    trg_rhs_PI(eeta, k, Om10, Om11, c.sw_nl, y, A14, dy);
+#pragma unroll
+    for (int j = 0; j < N_UP + N_UI; j++) db[(long long)j * nk] = dy[j];
+  }
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    double Q[8], R[8], dQ[8];
+    const int j0 = N_UP + N_UI + 8 * l;
+    if (c.sw_nl && evolve_Q) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) Q[j] = yb[(long long)(j0 + j) * nk];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double r = s1[(long long)(N_UI + 8 * l + j) * nk];
+        R[j] = one_loop ? pre * fp[r24_fpow(8 * l + j)] * r : r;
+      }
+      trg_rhs_Q(eeta, Om10, Om11, Q, R, dQ);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) dQ[j] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) db[(long long)(j0 + j) * nk] = dQ[j];
+  }
 }
 
 // ---------------------------------------------------------------------------- k_combine

@@ -12,8 +12,10 @@
 
 #ifdef __CUDACC__
 #define RT_HD __host__ __device__ __forceinline__
+#define RT_UNROLL _Pragma("unroll")
 #else
 #define RT_HD inline
+#define RT_UNROLL
 #endif
 
 namespace rtrg {
@@ -836,21 +838,22 @@ RT_HD void unique_abcdef(int j, int *a, int *c, int *d, int *b, int *e, int *f) 
   *a = hi; *c = hi; *d = 1; *b = (bef >> 2) & 1; *e = (bef >> 1) & 1; *f = bef & 1;
 }
 
-// y[41] -> dy[41] for one k.  A14: the 14 unique A_{acd,bef}; R24: R^ell_{abc}.
-// Om10 = Omega(1,0), Om11 = Omega(1,1) (rt:1395-1401).  evolve_Q: rt:1516.
-RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonlinear, int evolve_Q,
-                       const double *y, const double *A14, const double *R24, double *dy) {
-  // Omega(i,j) (rt:1383-1411) without a local table
+// Omega(i,j) (rt:1383-1411) without a local table
 #define RT_OM(i, j) ((i) == 0 ? ((j) == 0 ? 1.0 : -1.0) : ((j) == 0 ? Om10 : Om11))
-  const double eeta = exp(eta);
+// ln P_ab (3) and I_acd,bef (14): y17 = y[0..17), A14 = unique A_acd,bef, dy17 out (rt:1449-1513)
+RT_HD void trg_rhs_PI(double eeta, double k, double Om10, double Om11, int nonlinear, const double *y,
+                      const double *A14, double *dy) {
   const double P[3] = {exp(y[0]), exp(y[1]), exp(y[2])};
   double dP[3] = {0, 0, 0};
+  RT_UNROLL
   for (int c = 0; c < 2; c++) {
     dP[0] -= RT_OM(0, c) * P[c] + RT_OM(0, c) * P[c];
     dP[1] -= RT_OM(0, c) * P[c + 1] + RT_OM(1, c) * P[c];
     dP[2] -= RT_OM(1, c) * P[c + 1] + RT_OM(1, c) * P[c + 1];
     if (nonlinear) {
+      RT_UNROLL
       for (int d = 0; d < 2; d++) {
+        RT_UNROLL
         for (int q = 0; q < 3; q++) {
           const int a = (q > 0), b = (q > 1);  // (a,b) = 00, 10, 11
           const int s0 = i64_slot(nAI(a, c, d, b, c, d)), s1 = i64_slot(nAI(b, c, d, a, c, d));
@@ -865,12 +868,15 @@ RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonli
   dy[2] = dP[2] / P[2];
   if (dy[2] < -10.0) dy[2] = -10.0;  // rt:1488-1491
   if (dy[2] > 10.0) dy[2] = 10.0;
-  for (int j = N_UP; j < N_U; j++) dy[j] = 0;
+  RT_UNROLL
+  for (int j = N_UP; j < N_UP + N_UI; j++) dy[j] = 0;
   if (!nonlinear) return;
+  RT_UNROLL
   for (int j = 0; j < N_UI; j++) {
     int a, c, d, b, e, f;
     unique_abcdef(j, &a, &c, &d, &b, &e, &f);
     double v = 2.0 * eeta * A14[j];
+    RT_UNROLL
     for (int g = 0; g < 2; g++) {
       const int s1 = i64_slot(nAI(a, c, d, g, e, f)), s2 = i64_slot(nAI(a, c, d, b, g, f)),
                 s3 = i64_slot(nAI(a, c, d, b, e, g));
@@ -880,21 +886,34 @@ RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonli
     }
     dy[N_UP + j] = v;
   }
-  if (evolve_Q) {
-    for (int l = 0; l < 3; l++) {
-      const double *Q = y + N_UP + N_UI + 8 * l;
-      for (int a = 0; a < 2; a++)
-        for (int b = 0; b < 2; b++)
-          for (int c = 0; c < 2; c++) {
-            const int j = 4 * a + 2 * b + c;
-            double v = 2.0 * eeta * R24[8 * l + j];
-            for (int d = 0; d < 2; d++)
-              v += -RT_OM(a, d) * Q[4 * d + 2 * b + c] - RT_OM(b, d) * Q[4 * a + 2 * d + c] -
-                   RT_OM(c, d) * Q[4 * a + 2 * b + d];
-            dy[N_UP + N_UI + 8 * l + j] = v;
-          }
-    }
-  }
+}
+// one multipole of Q^l_abc: Q, R, dQ of length 8 (rt:1516-1539)
+RT_HD void trg_rhs_Q(double eeta, double Om10, double Om11, const double *Q, const double *R, double *dQ) {
+  RT_UNROLL
+  for (int a = 0; a < 2; a++)
+    RT_UNROLL
+    for (int b = 0; b < 2; b++)
+      RT_UNROLL
+      for (int c = 0; c < 2; c++) {
+        const int j = 4 * a + 2 * b + c;
+        double v = 2.0 * eeta * R[j];
+        RT_UNROLL
+        for (int d = 0; d < 2; d++)
+          v += -RT_OM(a, d) * Q[4 * d + 2 * b + c] - RT_OM(b, d) * Q[4 * a + 2 * d + c] -
+               RT_OM(c, d) * Q[4 * a + 2 * b + d];
+        dQ[j] = v;
+      }
+}
+// y[41] -> dy[41] for one k.  A14: the 14 unique A_{acd,bef}; R24: R^ell_{abc}.
+// Om10 = Omega(1,0), Om11 = Omega(1,1) (rt:1395-1401).  evolve_Q: rt:1516.
+RT_HD void trg_rhs_row(double eta, double k, double Om10, double Om11, int nonlinear, int evolve_Q,
+                       const double *y, const double *A14, const double *R24, double *dy) {
+  const double eeta = exp(eta);
+  trg_rhs_PI(eeta, k, Om10, Om11, nonlinear, y, A14, dy);
+  for (int j = N_UP + N_UI; j < N_U; j++) dy[j] = 0;
+  if (nonlinear && evolve_Q)
+    for (int l = 0; l < 3; l++)
+      trg_rhs_Q(eeta, Om10, Om11, y + N_UP + N_UI + 8 * l, R24 + 8 * l, dy + N_UP + N_UI + 8 * l);
 }
 
 #undef RT_OM
