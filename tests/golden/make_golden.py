@@ -27,7 +27,8 @@ if __name__ == "__main__":
         conftest.run_oracle_stage(d1, os.path.join(HERE, "example1_stage_1loop_nk256.npz"),
                                   lib="libredtime_stage_nk256.so", light=True)
         for tag, binary, d in (("nk256_1loop", "redTime_nk256", d1), ("nk256_full", "redTime_nk256", d2),
-                               ("hiacc_full", "redTime_hiacc", d2), ("printall_1loop", "redTime_printall", d1)):
+                               ("hiacc_full", "redTime_hiacc", d2), ("printall_1loop", "redTime_printall", d1),
+                               ("HIGH_ACCURACY_1loop", "redTime_HIGH_ACCURACY", d1)):
             txt = conftest.run_oracle_binary(d, binary=binary)
             with gzip.open(os.path.join(HERE, "example1_oracle_%s.dat.gz" % tag), "wt") as f:
                 f.write(txt)
