@@ -214,7 +214,7 @@ static std::string table_cache_path(const GridSpec &g) {
     return "";
   }
   char name[160];
-  std::snprintf(name, sizeof name, "/T_v1_nk%d_%.17g_%.17g.bin", g.nk, g.kmin, g.kmax);
+  std::snprintf(name, sizeof name, "/T_v2_nk%d_%.17g_%.17g.bin", g.nk, g.kmin, g.kmax);
   return d + name;
 }
 static double table_checksum(const std::vector<double> &a, const std::vector<double> &b, const std::vector<double> &c) {
@@ -229,7 +229,7 @@ static bool load_table_cache(const std::string &path, const GridSpec &g, std::ve
   FILE *f = std::fopen(path.c_str(), "rb");
   if (!f) return false;
   TableCacheHeader h;
-  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTRGTAB", 8) == 0 && h.version == 1 &&
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTRGTAB", 8) == 0 && h.version == 2 &&
             h.nk == g.nk && h.np == g.np && h.nsup == g.nsup && h.kmin == g.kmin && h.kmax == g.kmax &&
             (size_t)h.n_tc == Tc.size() && (size_t)h.n_tlo == Tlo.size() && (size_t)h.n_kfac == kfac.size();
   ok = ok && std::fread(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size();
@@ -253,7 +253,7 @@ static void save_table_cache(const std::string &path, const GridSpec &g, const s
   TableCacheHeader h;
   std::memset(&h, 0, sizeof h);
   std::memcpy(h.magic, "RTRGTAB", 8);
-  h.version = 1, h.nk = g.nk, h.np = g.np, h.nsup = g.nsup;
+  h.version = 2, h.nk = g.nk, h.np = g.np, h.nsup = g.nsup;
   h.n_tc = (int)Tc.size(), h.n_tlo = (int)Tlo.size(), h.n_kfac = (int)kfac.size();
   h.kmin = g.kmin, h.kmax = g.kmax, h.kfac_lo = kfac_lo, h.checksum = table_checksum(Tc, Tlo, kfac);
   bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size() &&
@@ -391,7 +391,8 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
           const int v = ((vv + UMIN) % np + np) % np;
           for (int uu = 0; uu < NU; uu++) {
             const int u = ((uu + UMIN) % np + np) % np;
-            dst[(size_t)vv * tb.ldT + uu] = T[(size_t)u * np + v];
+            // two consecutive beta-side lags share one 16-byte element: [vv/2][uu][vv&1]
+            dst[((size_t)(vv >> 1) * tb.ldT + uu) * 2 + (vv & 1)] = T[(size_t)u * np + v];
           }
         }
         for (int i = 0; i < nk; i++) kfac[(size_t)n * nk + i] = kf[g.nshift + i];

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(TPB, MINB)
   const int tu = chunk * TPB + tid;
   const bool active = tu < tb.NV;
   const int tuc = active ? tu : tb.NV - 1;
-  const double *Tp = tb.Tc + ((size_t)n * tb.NUp + i0) * ldT + i0 + tuc;
+  // T stream: 16-byte elements holding two consecutive beta-side lags (LDG.128, coalesced in u)
+  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tuc;
   const double *s_c[NCD];
 #pragma unroll
   for (int c = 0; c < NCD; c++) s_c[c] = s_a + item.cd[c] * LP;
@@ -179,7 +180,11 @@ __global__ void __launch_bounds__(TPB, MINB)
     for (int c = 0; c < NCD; c++) acc[r][c] = 0.0;
   double tcur[VC], tnxt[VC];
 #pragma unroll
-  for (int s = 0; s < VC; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
+  for (int s = 0; s < VC; s += 2) {
+    const double2 t2 = __ldg(Tp + (size_t)(s / 2) * ldT);
+    tcur[s] = t2.x;
+    tcur[s + 1] = t2.y;
+  }
 
   mbar_wait(&mbar, 0);
 
@@ -187,9 +192,13 @@ __global__ void __launch_bounds__(TPB, MINB)
   constexpr int NW = (VC + R) / 2;  // double2 loads covering the VC + R - 1 window values
   for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
     if (tv0 + VC < NVp) {
-      const double *Tn = Tp + (size_t)(tv0 + VC) * ldT;
+      const double2 *Tn = Tp + (size_t)((tv0 + VC) / 2) * ldT;
 #pragma unroll
-      for (int s = 0; s < VC; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
+      for (int s = 0; s < VC; s += 2) {
+        const double2 t2 = __ldg(Tn + (size_t)(s / 2) * ldT);
+        tnxt[s] = t2.x;
+        tnxt[s + 1] = t2.y;
+      }
     }
 #pragma unroll
     for (int c = 0; c < NCD; c++) {
@@ -307,7 +316,8 @@ __global__ void __launch_bounds__(TPB, 2)
   const int tu = chunk * TPB + tid;
   const bool active = tu < tb.NV;
   const int tuc = active ? tu : tb.NV - 1;
-  const double *Tp = tb.Tc + ((size_t)n * tb.NUp + i0) * ldT + i0 + tuc;
+  // T stream: 16-byte elements holding two consecutive beta-side lags (LDG.128, coalesced in u)
+  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tuc;
   const double *s_c[NS];
 #pragma unroll
   for (int q = 0; q < NS; q++) s_c[q] = s_a + (q * 3 + cd_q[q]) * LP;
@@ -319,7 +329,11 @@ __global__ void __launch_bounds__(TPB, 2)
     for (int q = 0; q < NS; q++) acc[r][q] = 0.0;
   double tcur[VC], tnxt[VC];
 #pragma unroll
-  for (int s = 0; s < VC; s++) tcur[s] = __ldg(Tp + (size_t)s * ldT);
+  for (int s = 0; s < VC; s += 2) {
+    const double2 t2 = __ldg(Tp + (size_t)(s / 2) * ldT);
+    tcur[s] = t2.x;
+    tcur[s + 1] = t2.y;
+  }
 
   mbar_wait(&mbar, 0);
 
@@ -327,9 +341,13 @@ __global__ void __launch_bounds__(TPB, 2)
   constexpr int NW = (VC + R) / 2;
   for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
     if (tv0 + VC < NVp) {
-      const double *Tn = Tp + (size_t)(tv0 + VC) * ldT;
+      const double2 *Tn = Tp + (size_t)((tv0 + VC) / 2) * ldT;
 #pragma unroll
-      for (int s = 0; s < VC; s++) tnxt[s] = __ldg(Tn + (size_t)s * ldT);
+      for (int s = 0; s < VC; s += 2) {
+        const double2 t2 = __ldg(Tn + (size_t)(s / 2) * ldT);
+        tnxt[s] = t2.x;
+        tnxt[s + 1] = t2.y;
+      }
     }
 #pragma unroll
     for (int q = 0; q < NS; q++) {

@@ -15,7 +15,7 @@
 //                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
 //   inputs             in     [sum over cosmologies of 3 nT + n_z + n_kb + 2 n_z n_kb]
 //                                                    raw CAMB columns, transformed in place
-//   weight tables      Tc     [14][NUp][ldT]         compact circulant kernels (L2 resident)
+//   weight tables      Tc     [14][NUp/2][ldT][2]    compact circulant kernels (L2 resident)
 #pragma once
 #include "rtrg_math.h"
 #ifdef __CUDACC__
@@ -45,7 +45,7 @@ struct IntegralTabs {
   int nchunk;  // CTAs along the lag dimension
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
-  const double *Tc;    // [14][NUp][ldT]  Tc[n][v''][u''] = T_n[u][v]
+  const double *Tc;    // [14][NUp/2][ldT][2]  Tc[n][v''/2][u''][v''&1] = T_n[u][v] (16-byte pairs in v)
   const double *Tlo;   // [nsup][nsup]    kernel 0 at the low-k row nloMR (reversed indices)
   const double *kfac;  // [14][nk]
   const double *G;     // [7][2np-1]
