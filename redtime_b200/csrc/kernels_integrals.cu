@@ -1,21 +1,24 @@
 // Kernel family (1): the 1-loop mode-coupling integrals as dense quadratures over the
 // extrapolated log-k power spectrum (replaces redTime.cc:740-1282).
 //
-//   k_extrap    Pab extrapolation + window (rt:181-232, 772-778)            HBM/latency bound
-//   k_bilinear  J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]      FP64 FMA pipe bound
-//   k_jlo       J_0 at the low-k row nloMR (rt:1252,1267-1272)
-//   k_pz        P13-type log-convolutions PZ_n (rt:689-727)
-//   k_assemble  A_{acd,bef}, R^l_{abc}, P_T,jm, P_MR,n from the table of assembly_table.cc
+//   k_extrap           Pab extrapolation + window (rt:181-232, 772-778)        HBM/latency bound
+//   k_bilinear(_packed) J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]   FP64 FMA pipe bound
+//   k_compact          list of the cosmologies a launch is masked in for
+//   k_jlo              J_0 at the low-k row nloMR (rt:1252,1267-1272)
+//   k_pz               P13-type log-convolutions PZ_n (rt:689-727)
+//   k_assemble         A_{acd,bef}, R^l_{abc}, P_T,jm, P_MR,n from the table of assembly_table.cc
 //
 // k_bilinear design (sm_100a): one CTA owns BIL_R = 8 consecutive output wavenumbers of one
-// kernel n of one cosmology.  Because T_n is circulant, rows i0..i0+7 read the same
-// (nsup+7)^2 window of T_n shifted along the diagonal, so each T element fetched from L2
-// feeds 8 rows x 3 spectra = 24 DFMAs.  The three spectra P q^2 (reversed and zero padded,
-// 8 KB) are staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); every
-// thread owns one alpha-side lag u, streams its T column with coalesced 8-byte loads that
-// are software-prefetched one 8-lag chunk ahead, and reads the beta-side window from
-// shared memory as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles.
-// Algorithmic work per (cosmology, n): 2*9*nk*nsup^2 FLOP; executed: 2*3*nk*(nsup+7)^2.
+// kernel n and three slots, a slot being a (cosmology, beta-side spectrum) pair.  Because T_n is
+// circulant, rows i0..i0+7 read the same (nsup+7)^2 window of T_n shifted along the diagonal,
+// so each T element fetched from L2 feeds 8 rows x 3 slots = 24 DFMAs.  The spectra P q^2 of
+// the slots' cosmologies (reversed and zero padded, 8 KB each) are staged in shared memory by
+// TMA bulk copies (cp.async.bulk + mbarrier); every thread owns one alpha-side lag u, streams
+// its T column with coalesced 16-byte loads (two beta-side lags per element) that are
+// software-prefetched one 8-lag chunk ahead, and reads the beta-side window from shared memory
+// as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles (recursive halving).
+// Only the (kernel, spectrum) sets the requested output groups consume are computed; one set
+// is nk (2 nsup^2 + 6 nsup) FLOP, executed 2 nk (nsup+7)^2.
 #include <cstdint>
 #include <cstdlib>
 
