@@ -1,6 +1,6 @@
 // Scalar building blocks of the Time-RG hot path, written once as __host__ __device__
 // inline functions.  The CUDA kernels (kernels_*.cu) are thin parallel drivers around
-// these; tests/harness/ compiles the same header with g++ to check the arithmetic against
+// these; tests/harness/math_harness.cc compiles the same header with g++ to check the arithmetic against
 // the oracle on machines without a GPU (test infrastructure only -- the shipped library
 // has no CPU execution path).
 //
