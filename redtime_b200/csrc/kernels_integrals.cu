@@ -19,6 +19,7 @@
 // as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles (recursive halving).
 // Only the (kernel, spectrum) sets the requested output groups consume are computed; one set
 // is nk (2 nsup^2 + 6 nsup) FLOP, executed 2 nk (nsup+7)^2.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
@@ -124,142 +125,21 @@ __device__ __forceinline__ void warp_sum_multi(double (&v)[V], int lane) {
   }
 }
 
-// One work item of a k_bilinear launch: kernel n applied to the beta-side spectra cd[0..NCD).
+// One work item of a k_bilinear launch: kernel n applied to the beta-side spectra cd[0..ncd).
 // Only the (kernel, spectrum) combinations the requested outputs consume are computed
 // (assembly_needs): e.g. the RHS needs A and R = all of J but only 3 of the 7 Jn0 kernels,
 // the default output columns need P_T,jm = 12 kernels x 2 spectra.  replicate: the three
 // spectra are identical (1-loop cache at z1l, rt:1303-1305), one product serves all 9 pairs.
 struct BilItem {
-  short n, cd[3];
+  short n, ncd, cd[3];
 };
 struct BilLaunch {
   BilItem it[N_JKERN];
   int replicate;
 };
 
-// R: output rows per CTA; TPB: threads (one alpha-side lag each); MINB: CTAs per SM the
-// register budget is tuned for; VC: beta-side lags per software-pipelined chunk; NCD: number of
-// beta-side spectra of every item of this launch.
-template <int R, int TPB, int MINB, int VC, int NCD>
-__global__ void __launch_bounds__(TPB, MINB)
-    k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
-               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int row0,
-               const int *__restrict__ mask) {
-  const int e = blockIdx.z;
-  if (mask && !mask[e]) return;
-  const BilItem item = L.it[blockIdx.y];
-  const int n = item.n;
-  if (n >= 7 && !cosmo[e].sw_pr) return;  // Jn0 only feeds the RSD terms (rt:804)
-  const int rb = blockIdx.x / tb.nchunk, chunk = blockIdx.x - rb * tb.nchunk;
-  extern __shared__ __align__(128) double sm[];
-  double *s_a = sm;                // [3][LP]
-  double *s_red = sm + 3 * tb.LP;  // [TPB/32][9R]
-  __shared__ __align__(8) unsigned long long mbar;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int LP = tb.LP, ldT = tb.ldT;
-  const uint32_t bytes = 3u * (uint32_t)LP * 8u;
-
-  if (tid == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&mbar, bytes);
-    tma_bulk_g2s(s_a, Prev + (long long)e * 3 * LP, bytes, &mbar);
-  }
-
-  const int i0 = row0 + rb * R;
-  const int tu = chunk * TPB + tid;
-  const bool active = tu < tb.NV;
-  const int tuc = active ? tu : tb.NV - 1;
-  // T stream: 16-byte elements holding two consecutive beta-side lags (LDG.128, coalesced in u)
-  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tuc;
-  const double *s_c[NCD];
-#pragma unroll
-  for (int c = 0; c < NCD; c++) s_c[c] = s_a + item.cd[c] * LP;
-
-  double acc[R][NCD];
-#pragma unroll
-  for (int r = 0; r < R; r++)
-#pragma unroll
-    for (int c = 0; c < NCD; c++) acc[r][c] = 0.0;
-  double tcur[VC], tnxt[VC];
-#pragma unroll
-  for (int s = 0; s < VC; s += 2) {
-    const double2 t2 = __ldg(Tp + (size_t)(s / 2) * ldT);
-    tcur[s] = t2.x;
-    tcur[s + 1] = t2.y;
-  }
-
-  mbar_wait(&mbar, 0);
-
-  const int NVp = tb.NVp;
-  constexpr int NW = (VC + R) / 2;  // double2 loads covering the VC + R - 1 window values
-  for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
-    if (tv0 + VC < NVp) {
-      const double2 *Tn = Tp + (size_t)((tv0 + VC) / 2) * ldT;
-#pragma unroll
-      for (int s = 0; s < VC; s += 2) {
-        const double2 t2 = __ldg(Tn + (size_t)(s / 2) * ldT);
-        tnxt[s] = t2.x;
-        tnxt[s + 1] = t2.y;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NCD; c++) {
-      // window w[q] = arev_c[tv0 + q - (R-1)], q in [0, VC+R-1): 16-byte broadcast loads
-      double w[2 * NW];
-      const double2 *wp = reinterpret_cast<const double2 *>(s_c[c] + tv0);
-#pragma unroll
-      for (int q = 0; q < NW; q++) {
-        const double2 v = wp[q];
-        w[2 * q] = v.x;
-        w[2 * q + 1] = v.y;
-      }
-#pragma unroll
-      for (int s = 0; s < VC; s++)
-#pragma unroll
-        for (int r = 0; r < R; r++) acc[r][c] = fma(tcur[s], w[s - r + R - 1], acc[r][c]);
-    }
-#pragma unroll
-    for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
-  }
-
-  // alpha side: out[ab][c][r] = sum_u arev_ab[u - r] * S_u[r][c].  Eight rows at a time go
-  // through the halving reduction; lane 4*r then holds row r.
-  static_assert(R == 8, "the epilogue reduction is written for 8 rows per CTA");
-  const int nab = L.replicate ? 1 : 3;
-  for (int ab = 0; ab < nab; ab++) {
-    double m[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) m[r] = active ? s_a[ab * LP + (R - 1) + tu - r] : 0.0;
-#pragma unroll
-    for (int c = 0; c < NCD; c++) {
-      double prod[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) prod[r] = m[r] * acc[r][c];
-      warp_sum_multi<R>(prod, lane);
-      if ((lane & 3) == 0) s_red[warp * (9 * R) + (ab * 3 + c) * R + (lane >> 2)] = prod[0];
-    }
-  }
-  __syncthreads();
-  if (tid < 9 * R) {
-    const int slot = tid / R, r = tid - slot * R, ab = slot / 3, c = slot - 3 * ab;
-    if (ab < nab && c < NCD) {
-      double s = 0.0;
-#pragma unroll 1
-      for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
-      double *dst = Jpart + (((long long)e * N_JKERN + n) * tb.nchunk + chunk) * 9 * tb.nk + i0 + r;
-      if (L.replicate) {
-#pragma unroll
-        for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
-      } else {
-        dst[(long long)(ab * 3 + item.cd[c]) * tb.nk] = s;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------- k_bilinear_packed
-// Batch variant: a CTA always carries THREE (cosmology, beta-side spectrum) slots through the
+// ---------------------------------------------------------------------------- k_bilinear
+// A CTA always carries THREE (cosmology, beta-side spectrum) slots through the
 // same T stream, taken from consecutive entries of the list {active cosmologies} x {spectra of
 // the item}, so every T element feeds 8 rows x 3 slots = 24 DFMAs whatever the number of spectra
 // the item needs (1 for the 1-loop cache, 2 for most P_T,jm kernels, 3 inside the RHS).
@@ -277,14 +157,16 @@ __global__ void k_compact(const int *__restrict__ mask, int B, int *__restrict__
   if (lane == 0) *nact = off;
 }
 
+// R: output rows per CTA; TPB: threads (one alpha-side lag each); VC: beta-side lags per
+// software-pipelined chunk.  Grid: (row blocks x lag chunks, items, ceil(B * 3 / 3)).
 template <int R, int TPB, int VC>
 __global__ void __launch_bounds__(TPB, 2)
-    k_bilinear_packed(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
-                      double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int ncd, int row0,
-                      const int *__restrict__ act, const int *__restrict__ nact) {
+    k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int row0,
+               const int *__restrict__ act, const int *__restrict__ nact) {
   constexpr int NS = 3;
   const BilItem item = L.it[blockIdx.y];
-  const int n = item.n;
+  const int n = item.n, ncd = item.ncd;
   const int nslots = (*nact) * ncd;
   const int slot0 = NS * blockIdx.z;
   if (slot0 >= nslots) return;
@@ -528,19 +410,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------- launchers
-enum { BIL_TPB = 352, BIL_PACK_MIN_B = 6 };  // batches of >= 6 cosmologies use the packed kernel
+enum { BIL_TPB = 352 };
 
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
-  return (size_t)(3 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
-}
-
-template <int NCD>
-static void launch_bilinear_class(const IntegralTabs &tb, const Batch &S, const BilLaunch &L, int nitems, int row0,
-                                  int nrows, const int *mask, cudaStream_t st) {
-  if (nitems == 0) return;
-  dim3 g((nrows / BIL_R) * tb.nchunk, nitems, S.B);
-  const size_t smem = bilinear_smem_bytes(tb);
-  k_bilinear<BIL_R, BIL_TPB, 2, 8, NCD><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0, mask);
+  return (size_t)(9 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
 }
 
 // Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
@@ -551,10 +424,9 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
                      cudaStream_t st, Profiler *prof) {
   const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
   int launches = 0;
-  // work items by number of beta-side spectra
-  BilLaunch L[3];
-  int nit[3] = {0, 0, 0};
-  int units = 0;
+  // work items: kernel n with the beta-side spectra the requested groups consume
+  BilLaunch L;
+  int nitems = 0, units = 0;
   for (int n = 0; n < N_JKERN; n++) {
     int need = 0;
     for (int gi = 0; gi < 4; gi++)
@@ -564,14 +436,14 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     if (identical) need = 1;
     BilItem it;
     it.n = (short)n;
-    int ncd = 0;
+    it.ncd = 0;
     for (int c = 0; c < 3; c++)
-      if (need & (1 << c)) it.cd[ncd++] = (short)c;
-    for (int c = ncd; c < 3; c++) it.cd[c] = 0;
-    L[ncd - 1].it[nit[ncd - 1]++] = it;
-    units += ncd;
+      if (need & (1 << c)) it.cd[it.ncd++] = (short)c;
+    for (int c = it.ncd; c < 3; c++) it.cd[c] = 0;
+    L.it[nitems++] = it;
+    units += it.ncd;
   }
-  for (int c = 0; c < 3; c++) L[c].replicate = identical ? 1 : 0;
+  L.replicate = identical ? 1 : 0;
   {
     dim3 g((tb.np + 127) / 128, B);
     RT_TIC(prof, PC_EXTRAP, st);
@@ -580,24 +452,17 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     launches++;
   }
   RT_TIC(prof, PC_BILINEAR, st);
-  if (B >= BIL_PACK_MIN_B) {
-    // batch: three (cosmology, spectrum) slots per CTA
-    k_compact<<<1, 32, 0, st>>>(mask, B, S.act, S.nact);
+  k_compact<<<1, 32, 0, st>>>(mask, B, S.act, S.nact);
+  launches++;
+  if (nitems) {
+    // z covers the slot triples of the widest item of this launch; CTAs beyond an item's own
+    // slot count exit at once
+    int maxncd = 1;
+    for (int i = 0; i < nitems; i++) maxncd = std::max(maxncd, (int)L.it[i].ncd);
+    dim3 g((nrows / BIL_R) * tb.nchunk, nitems, (B * maxncd + 2) / 3);
+    k_bilinear<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0,
+                                                                             S.act, S.nact);
     launches++;
-    const size_t smem = (size_t)(9 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
-    for (int c = 0; c < 3; c++) {
-      if (!nit[c]) continue;
-      const int ncd = c + 1;
-      dim3 g((nrows / BIL_R) * tb.nchunk, nit[c], (B * ncd + 2) / 3);
-      k_bilinear_packed<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, smem, st>>>(tb, S.cosmo, S.Prev, S.Jpart, L[c], ncd, row0,
-                                                                      S.act, S.nact);
-      launches++;
-    }
-  } else {
-    launch_bilinear_class<1>(tb, S, L[0], nit[0], row0, nrows, mask, st);
-    launch_bilinear_class<2>(tb, S, L[1], nit[1], row0, nrows, mask, st);
-    launch_bilinear_class<3>(tb, S, L[2], nit[2], row0, nrows, mask, st);
-    launches += (nit[0] > 0) + (nit[1] > 0) + (nit[2] > 0);
   }
   RT_TOC(prof, st);
   if (groups & GRP_PMR) {
@@ -632,12 +497,9 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 }
 
 int integrals_configure() {
-  // opt in to the dynamic shared memory the bilinear kernel may need for large grids
-  const int sm = 96 * 1024;
-  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  cudaFuncSetAttribute(k_bilinear_packed<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 2, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  // opt in to the dynamic shared memory the bilinear kernel needs on large grids
+  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   110 * 1024);
 }
 
 }  // namespace rtrg
