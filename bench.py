@@ -57,6 +57,7 @@ def parse_args():
                     help="keep the synthetic input tables in pageable host memory (the library then stages "
                          "them through its own page-locked arena); default: page-locked inputs, direct H2D")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: concurrent processes (0 = host cores)")
+    ap.add_argument("--v-split", type=int, default=0, help="kshard: rtrg_config.v_split (0 = by GPU count)")
     ap.add_argument("--workload", default="batch", choices=["batch", "kshard"],
                     help="batch: cosmologies sharded over GPUs, no collective (headline); kshard: ONE "
                          "high-accuracy nk=256 full Time-RG cosmology (BASELINE configs[2]) with its k rows "
@@ -442,8 +443,11 @@ def run_kshard(a, rank, world, local_rank):
     nk = 256
     c = wl.load_example1(a.subsample)
     c["switches"] = [1, 0, 1, 1]
+    # split the beta-side lags as well once the rows per rank are few: keeps every SM busy and
+    # shortens the serial chain of a CTA (rtrg_config.v_split; round-off level change only)
+    v_split = a.v_split if a.v_split else (1 if world == 1 else 2 if world == 2 else 4)
     h = rt.RedTimeB200(device=local_rank, nk=nk, beta_kmin=1e-5, beta_kmax=20.0, n_lnk=1000, a_early=1e-50,
-                       k_shards=world, k_rank=rank)
+                       k_shards=world, k_rank=rank, v_split=v_split)
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     if world > 1:
@@ -524,7 +528,8 @@ def run_kshard(a, rank, world, local_rank):
             "dtype": "f64", "data": "example-1 CAMB tables (the reference's examples/1_redTime)",
             "config": {"workload": "BASELINE configs[2]: single cosmology, nk=256, beta clamp [1e-5,20], n_lnk=1000, "
                                    "a_early=1e-50, switches 1 0 1 1, k rows sharded over %d GPU(s), NCCL all-gather of "
-                                   "ln P_ab per RHS stage + max-reduce of the error norm per attempt" % world,
+                                   "ln P_ab per RHS stage + max-reduce of the error norm per attempt, v_split=%d"
+                                   % (world, v_split),
                        "l2": "256 MiB flush before every step"},
             "clocks": clk,
             "e2e": {"value": n_out * steps / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / steps,

@@ -53,6 +53,10 @@ typedef struct rtrg_config {
   int max_attempts;    /* 100000: cap on RKF45 step attempts per cosmology          */
   int k_shards;        /* 1; >1: this handle owns k-rows [k_rank*nk/k_shards, ...)   */
   int k_rank;          /* 0                                                         */
+  int v_split;         /* 1: CTAs per row block along the beta-side lags of the bilinear
+                          quadrature.  > 1 shortens the serial work of a CTA when the grid is too
+                          small to fill the GPU (one cosmology, k-sharded ranks); the partial sums
+                          are added in a different order, so results move by round-off       */
   int reduce_beta;     /* 0: the full Beta_P(a,k) tables go to the device (every hook works);
                           1: the host sends only what rtrg_run consumes -- beta at a = 1 and the
                              table pre-reduced in k at the grid / growth wavenumbers (5x fewer

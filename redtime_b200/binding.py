@@ -25,7 +25,7 @@ class Config(C.Structure):
                 ("a_early", C.c_double), ("print_A", C.c_int), ("print_I", C.c_int),
                 ("print_Q", C.c_int), ("print_bias", C.c_int), ("device", C.c_int),
                 ("max_attempts", C.c_int), ("k_shards", C.c_int), ("k_rank", C.c_int),
-                ("reduce_beta", C.c_int)]
+                ("v_split", C.c_int), ("reduce_beta", C.c_int)]
 
 
 class _Cosmology(C.Structure):

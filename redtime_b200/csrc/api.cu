@@ -323,6 +323,7 @@ void rtrg_default_config(rtrg_config *cfg) {
   cfg->max_attempts = 100000;
   cfg->k_shards = 1;
   cfg->k_rank = 0;
+  cfg->v_split = 1;
 }
 
 const char *rtrg_last_error(void) { return g_err.c_str(); }
@@ -333,7 +334,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   *out = nullptr;
   if (cfg->nk < 16 || cfg->nk % 16 || !(cfg->kmin > 0) || !(cfg->kmax > cfg->kmin) || cfg->n_lnk < 3 ||
       cfg->n_lna < 3 || cfg->k_shards < 1 || cfg->k_rank < 0 || cfg->k_rank >= cfg->k_shards ||
-      (cfg->nk / BIL_R) % cfg->k_shards)
+      (cfg->nk / BIL_R) % cfg->k_shards || cfg->v_split < 1 || cfg->v_split > 16)
     return fail(RTRG_EINVAL, "invalid configuration");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -372,6 +373,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   tb.NUp = nk - BIL_R + tb.NVp;
   tb.ldT = (nk + g.nsup - 1 + 7) / 8 * 8;
   tb.nchunk = (tb.NV + 352 - 1) / 352;
+  tb.vsplit = cfg->v_split;
   tb.dlnk = g.dlnk;
 
   // --- circulant kernels, built in parallel on the host, packed into the compact layout
@@ -901,7 +903,7 @@ int rtrg_prepare(rtrg_handle *h) {
     S.src = A.take<double>((size_t)B * N_SRC * nk);
     S.Prev = A.take<double>((size_t)B * 3 * tb.LP);
     S.P3 = A.take<double>((size_t)B * 3 * np);
-    S.Jpart = A.take<double>((size_t)B * N_JKERN * tb.nchunk * 9 * nk);
+    S.Jpart = A.take<double>((size_t)B * N_JKERN * tb.nchunk * tb.vsplit * 9 * nk);
     S.PZb = A.take<double>((size_t)B * N_ZKERN * 3 * nk);
     S.Jlo = A.take<double>(B);
     S.t = A.take<double>(B);

@@ -170,7 +170,10 @@ __global__ void __launch_bounds__(TPB, 2)
   const int nslots = (*nact) * ncd;
   const int slot0 = NS * blockIdx.z;
   if (slot0 >= nslots) return;
-  const int rb = blockIdx.x / tb.nchunk, chunk = blockIdx.x - rb * tb.nchunk;
+  // blockIdx.x = (row block, split of the beta-side lags, chunk of the alpha-side lags)
+  const int nch = tb.nchunk * tb.vsplit;
+  const int rb = blockIdx.x / nch, part = blockIdx.x - rb * nch;
+  const int vs = part / tb.nchunk, chunk = part - vs * tb.nchunk;
   extern __shared__ __align__(128) double sm[];
   double *s_a = sm;                     // [NS][3][LP]: the three spectra of each slot's cosmology
   double *s_red = sm + NS * 3 * tb.LP;  // [TPB/32][9R]
@@ -212,19 +215,23 @@ __global__ void __launch_bounds__(TPB, 2)
   for (int r = 0; r < R; r++)
 #pragma unroll
     for (int q = 0; q < NS; q++) acc[r][q] = 0.0;
+  // this CTA's share of the beta-side lags (v_split > 1 shortens the serial chain of a CTA when
+  // the grid is too small to fill the GPU: single cosmology, k-sharded ranks)
+  const int vlen = ((tb.NVp / VC + tb.vsplit - 1) / tb.vsplit) * VC;
+  const int tv_begin = vs * vlen, NVp = min(tb.NVp, tv_begin + vlen);
   double tcur[VC], tnxt[VC];
 #pragma unroll
   for (int s = 0; s < VC; s += 2) {
-    const double2 t2 = __ldg(Tp + (size_t)(s / 2) * ldT);
+    double2 t2 = make_double2(0.0, 0.0);
+    if (tv_begin < tb.NVp) t2 = __ldg(Tp + (size_t)((tv_begin + s) / 2) * ldT);  // (an empty split adds zeros)
     tcur[s] = t2.x;
     tcur[s + 1] = t2.y;
   }
 
   mbar_wait(&mbar, 0);
 
-  const int NVp = tb.NVp;
   constexpr int NW = (VC + R) / 2;
-  for (int tv0 = 0; tv0 < NVp; tv0 += VC) {
+  for (int tv0 = tv_begin; tv0 < NVp; tv0 += VC) {
     if (tv0 + VC < NVp) {
       const double2 *Tn = Tp + (size_t)((tv0 + VC) / 2) * ldT;
 #pragma unroll
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(TPB, 2)
       double s = 0.0;
 #pragma unroll 1
       for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
-      double *dst = Jpart + (((long long)e_q[q] * N_JKERN + n) * tb.nchunk + chunk) * 9 * tb.nk + i0 + r;
+      double *dst = Jpart + (((long long)e_q[q] * N_JKERN + n) * nch + part) * 9 * tb.nk + i0 + r;
       if (L.replicate) {
 #pragma unroll
         for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
@@ -371,8 +378,9 @@ __global__ void __launch_bounds__(256)
       const int iJ = (v < 63) ? v : v - 126;
       const int n = iJ / 9 + ((v < 63) ? 0 : 7), pair = iJ % 9;
       if (v < 63 || has_jn0) {
-        for (int ch = 0; ch < tb.nchunk; ch++)
-          x += Jpart[((((long long)e * N_JKERN + n) * tb.nchunk + ch) * 9 + pair) * tb.nk + i];
+        const int nch = tb.nchunk * tb.vsplit;
+        for (int ch = 0; ch < nch; ch++)
+          x += Jpart[((((long long)e * N_JKERN + n) * nch + ch) * 9 + pair) * tb.nk + i];
         x *= tb.kfac[n * tb.nk + i];
       }
     } else if (v < 126) {
@@ -459,7 +467,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     // slot count exit at once
     int maxncd = 1;
     for (int i = 0; i < nitems; i++) maxncd = std::max(maxncd, (int)L.it[i].ncd);
-    dim3 g((nrows / BIL_R) * tb.nchunk, nitems, (B * maxncd + 2) / 3);
+    dim3 g((nrows / BIL_R) * tb.nchunk * tb.vsplit, nitems, (B * maxncd + 2) / 3);
     k_bilinear<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0,
                                                                              S.act, S.nact);
     launches++;

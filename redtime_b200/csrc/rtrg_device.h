@@ -10,7 +10,7 @@
 //   growth rows        Grow, dDrow [B][n_lna+1][nk]; D0row [B][nk]
 //   integrals          Prev   [B][3][LP]             reversed, zero-padded P q^2 (TMA source)
 //                      P3     [B][3][np]             extrapolated, windowed spectra
-//                      Jpart  [B][14][nchunk][9][nk] partial bilinear sums
+//                      Jpart  [B][14][nchunk*vsplit][9][nk] partial bilinear sums
 //                      PZb    [B][7][3][nk]
 //                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
 //   inputs             in     [sum over cosmologies of 3 nT + n_z + n_kb + 2 n_z n_kb]
@@ -42,7 +42,8 @@ struct IntegralTabs {
   int LP;      // padded length of one reversed spectrum (even)
   int NUp;     // rows of the compact kernel table (>= nk + NVp)
   int ldT;     // leading dimension of the compact kernel table
-  int nchunk;  // CTAs along the lag dimension
+  int nchunk;  // CTAs along the alpha-side lag dimension
+  int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
   const double *Tc;    // [14][NUp/2][ldT][2]  Tc[n][v''/2][u''][v''&1] = T_n[u][v] (16-byte pairs in v)

@@ -78,3 +78,17 @@ def test_kshard_needs_a_transport(example1_dir):
     h.close()
     with pytest.raises(rt.RtrgError):
         rt.RedTimeB200(k_shards=3, k_rank=0)  # nk/8 = 16 rows blocks are not divisible by 3
+
+
+def test_v_split_changes_only_round_off(example1_full_dir):
+    """v_split > 1 splits the beta-side lags of a row block over several CTAs (shorter serial
+    chains for tiny grids); partial sums are added in another order."""
+    ref, hdr, cnt0 = run_single(example1_full_dir)
+    for vs in (2, 4, 16):
+        tab, _, cnt = run_single(example1_full_dir, v_split=vs)
+        assert (cnt["attempts"], cnt["rejected"]) == (cnt0["attempts"], cnt0["rejected"])
+        assert np.max(np.abs(tab[:, :, :10] / ref[:, :, :10] - 1)) < 2e-9
+    # and sharding with a split stays bit-identical to the unsharded run with the same split
+    ref4, _, _ = run_single(example1_full_dir, v_split=4)
+    res, _ = run_sharded(example1_full_dir, 2, v_split=4)
+    assert np.array_equal(res[0][0][0], ref4) and np.array_equal(res[1][0][0], ref4)
