@@ -405,7 +405,13 @@ def run_b200(a, rank, world, local_rank):
     achieved = flop_total / (ms_bil * 1e-3) * 1e-12 if ms_bil > 0 else 0.0
     sm_clk = 1.965e9
     roof = {"bound": "fp64", "kernel": "k_bilinear", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
+            "frac": achieved / peak if peak else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_bilinear launch from the committed
+            # ncu --set full capture (profiles/r01_k_bilinear_final_ncu.txt: 64 cosmologies x 42 sets =
+            # 74.3 GFLOP algorithmic): the 23.7 MB weight tables stream from L2, DRAM sees them once
+            "traffic": 22763264 + 177664,
+            "traffic_note": "bytes per launch of the ncu-captured launch (64 cosmologies x 42 matvec sets), not of "
+                            "the average bench launch; algorithmic FLOP per DRAM byte there = 3.2e3",
             "peak_source": "DFMA loop measured live by rtrg_bench_dfma (MEASURED_PEAKS.json has no FP64 figure); "
                            "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = %.1f TFLOP/s" % (148 * 64 * 2 * sm_clk * 1e-12),
             "launches": n_bil, "avg_launch_ms": ms_bil / max(n_bil, 1),
