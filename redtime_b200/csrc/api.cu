@@ -1070,7 +1070,11 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
 
   long long rounds = 0;
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
-  while (n_active > 0 && rounds < max_rounds) {
+  // One round = every unfinished cosmology attempts one RKF45 step or emits one table.  The
+  // launch sequence of a round is the same every time (what differs lives in device-side masks),
+  // so it is captured once into a CUDA graph and replayed: a round is ~25-60 launches (+ the NCCL
+  // exchanges when k-sharded), which is launch-latency bound for small batches.
+  auto round_body = [&]() -> int {
     ODE_LAUNCH(PC_CTRL, launch_ctrl_begin(S, st));
     if (h->any_1loop && grp_out(h))
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, grp_out(h), 0, st, h->prof);
@@ -1090,10 +1094,53 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     if (h->any_full)
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof);
     ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st));
-    CU(cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    return RTRG_OK;
+  };
+  // no graph while per-kernel timing is on (events between the nodes), for the host-driven
+  // loopback exchange, or when RTRG_NO_GRAPH is set
+  const bool use_graph = !h->prof && (!sharded || h->xch->capturable()) && !std::getenv("RTRG_NO_GRAPH");
+  cudaGraphExec_t gexec = nullptr;
+  long long launches_per_round = 0;
+  if (use_graph && n_active > 0 &&
+      cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();  // e.g. the legacy default stream cannot be captured: plain launches then
+  } else if (use_graph && n_active > 0) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = h->launches;
+    const int rc_body = round_body();
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    launches_per_round = h->launches - l0;
+    h->launches = l0;
+    if (rc_body != RTRG_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc_body;
+    }
+    if (ce != cudaSuccess) return fail(RTRG_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(RTRG_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+  }
+  while (n_active > 0 && rounds < max_rounds) {
+    if (gexec) {
+      const cudaError_t ge = cudaGraphLaunch(gexec, st);
+      if (ge != cudaSuccess) {
+        cudaGraphExecDestroy(gexec);
+        return fail(RTRG_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(ge));
+      }
+      h->launches += launches_per_round;
+    } else {
+      const int rc_body = round_body();
+      if (rc_body != RTRG_OK) return rc_body;
+    }
+    cudaError_t e1 = cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+    if (e1 != cudaSuccess) {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      return fail(RTRG_ECUDA, "round %lld: %s", rounds, cudaGetErrorString(e1));
+    }
     rounds++;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
   CU(cudaGetLastError());
   if (sharded) {  // every rank ends up with the complete tables
     std::vector<Segment> segs;

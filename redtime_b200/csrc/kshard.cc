@@ -67,6 +67,7 @@ class NcclExchange : public Exchange {
   }
   int nranks() const override { return nranks_; }
   int rank() const override { return rank_; }
+  bool capturable() const override { return true; }
   int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) override {
     ncclResult_t r = api_->GroupStart();
     for (const Segment &s : segs) {
@@ -155,6 +156,7 @@ class LoopbackExchange : public Exchange {
   }
   int nranks() const override { return g_->n; }
   int rank() const override { return rank_; }
+  bool capturable() const override { return false; }  // host-side rendezvous between the ranks
   int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) override {
     // my block must be complete before anybody reads it
     if (cudaStreamSynchronize(st) != cudaSuccess) return fail(err);

@@ -28,6 +28,8 @@ class Exchange {
   virtual ~Exchange() {}
   virtual int nranks() const = 0;
   virtual int rank() const = 0;
+  // true when allgather / allreduce only enqueue work on the stream (CUDA-graph capturable)
+  virtual bool capturable() const = 0;
   // in-place all-gather of every segment, ordered on `st`; returns 0 or sets err
   virtual int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) = 0;
   // in-place max over ranks of n unsigned 64-bit values (bit patterns of non-negative doubles)
