@@ -735,6 +735,12 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   }
   CU(cudaSetDevice(h->cfg.device));
   const size_t first = h->cos.size();
+  const size_t d_in_used0 = h->d_in_used, stage_used0 = h->stage.used;
+  auto roll_back = [&]() {  // leave the handle as it was before this call
+    h->cos.resize(first);
+    h->d_in_used = d_in_used0;
+    h->stage.used = stage_used0;
+  };
   // layout: the small tables of this call form one slice (mirrored in the arena), the big raw
   // tables of the direct cosmologies follow it
   size_t off = h->d_in_used, soff = h->stage.used;
@@ -749,7 +755,7 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   }
   if (soff > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
   if (h->stage.reserve(soff) != RTRG_OK) {
-    h->cos.resize(first);
+    roll_back();
     return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", soff * sizeof(double));
   }
   h->stage.used = soff;
@@ -759,12 +765,18 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     double *q = nullptr;
     const size_t ncap = h->d_in_used + h->d_in_used / 8;
     cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
-    if (e != cudaSuccess) return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      roll_back();
+      return fail(RTRG_ENOMEM, "cudaMalloc(%zu bytes): %s", ncap * sizeof(double), cudaGetErrorString(e));
+    }
     if (h->d_in) cudaFree(h->d_in);
     h->d_in = q;
     h->d_in_cap = ncap;
     int rc = upload_range(h, 0, first);  // the pool moved: what was sent before goes out again
-    if (rc) return rc;
+    if (rc) {
+      roll_back();
+      return rc;
+    }
   }
   // Staging runs on several host threads (the copies are memory-bound, one thread moves only
   // ~10 GB/s); every chunk is sent as soon as it is staged, so the PCIe transfer overlaps the
@@ -787,7 +799,11 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
       for (auto &t : th) t.join();
     }
     int rc = upload_range(h, first + c0, first + c1);
-    if (rc) return rc;
+    if (rc) {
+      cudaStreamSynchronize(h->copy_stream);
+      roll_back();
+      return rc;
+    }
   }
   h->prepared = h->uploaded = false;
   return RTRG_OK;
