@@ -106,3 +106,22 @@ def test_comment_lines_in_transfer_files(tmp_path):
     open(os.path.join(d, "camb_transfer_z3.dat"), "w").write("# comment\n" + open(os.path.join(d, "camb_transfer_z3.dat")).read())
     with pytest.raises(rt.RtrgError):
         rt.read_run_dir(d)
+
+
+def test_camb_modern_13_column_files(tmp_path):
+    """-DCAMB_MODERN in the reference (hdr:76-80): 13 columns per row, same k / CDM / baryon /
+    massive-nu positions.  Here: rtrg_read_run_dir(dir, camb_modern=1), RTRG_CAMB_MODERN=1."""
+    base = wl.load_example1(subsample=256)
+    c = wl.make_cosmologies(1, base)[0]
+    d = wl.write_run_dir(str(tmp_path / "c"), c)
+    for name in os.listdir(d):
+        if name.startswith("camb_transfer_z"):
+            t = np.loadtxt(os.path.join(d, name))
+            wide = np.hstack([t, np.full((t.shape[0], 6), 7.0)])
+            np.savetxt(os.path.join(d, name), wide, fmt="%.17e")
+    r = rt.read_run_dir(d, camb_modern=True)
+    for key in ("k_T", "Tc_T", "Tb_T", "Tc_b", "Tnu_b"):
+        assert np.array_equal(np.asarray(r[key]), np.asarray(c[key])), key
+    # read as 7-column files the rows no longer line up: the k lists of the files disagree
+    with pytest.raises(rt.RtrgError):
+        rt.read_run_dir(d, camb_modern=False)
