@@ -4,7 +4,8 @@
 // the GPU through the C-ABI, and prints the reference's stdout tables.  No argv is needed;
 // optional environment overrides expose the reference's compile-time constants:
 //   RTRG_NK, RTRG_DEVICE, RTRG_PRINTA/I/Q/BIAS, RTRG_HIACC=1 (beta clamp [1e-5,20],
-//   n_lnk=1000, a_early=1e-50), RTRG_CAMB_MODERN=1 (13-column transfer files).
+//   n_lnk=1000, a_early=1e-50), RTRG_HIGH_ACCURACY=1 (-DHIGH_ACCURACY: nk=512, RKF45 tolerances
+//   1e-15/1e-6), RTRG_CAMB_MODERN=1 (13-column transfer files).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -28,6 +29,9 @@ int main(int argc, char **argv) {
   cfg.print_bias = env_int("RTRG_PRINTBIAS", 0);
   if (env_int("RTRG_HIACC", 0)) {
     cfg.beta_kmin = 1e-5, cfg.beta_kmax = 20.0, cfg.n_lnk = 1000, cfg.a_early = 1e-50;
+  }
+  if (env_int("RTRG_HIGH_ACCURACY", 0)) {  // the reference's -DHIGH_ACCURACY (rt:90-94,141-145)
+    cfg.nk = 512, cfg.eps_abs = 1e-15, cfg.eps_rel = 1e-6;
   }
   std::printf("#cosmological_parameters: opening parameter file: params_redTime.dat\n");
   rtrg_run_inputs *in = nullptr;
