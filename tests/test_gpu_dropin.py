@@ -129,3 +129,25 @@ def test_emulator_goldens_massless_neutrinos(tmp_path):
             assert np.max(np.abs(tab[i, :, 2] / rec["f"][i] - 1)) < 1e-11, m
             assert abs(hd[i, 3] / rec["H"][i] - 1) < 1e-11
             assert not tab[i, :, 4:7].any()
+
+
+def test_cpp_batch_front_end(tmp_path, golden_example1):
+    """redTimeBatch_b200 <manifest>: the C++-only replacement of the runRedTimeBatch loop."""
+    from conftest import make_example1_dir
+    d1 = make_example1_dir(str(tmp_path / "M001"))
+    d2 = make_example1_dir(str(tmp_path / "M002"), switches=[1, 0, 1, 1])
+    (tmp_path / "manifest.txt").write_text("# models\nM001\n%s   # absolute path\n" % d2)
+    exe = os.path.join(ROOT, "redtime_b200", "redTimeBatch_b200")
+    p = subprocess.run([exe, str(tmp_path / "manifest.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "2 models, 0 failed" in p.stdout
+    hdr, arr = parse_tables(open(os.path.join(d1, "redTime_M001.dat")).read())
+    ghdr, gold = golden_example1
+    assert hdr == ghdr
+    assert np.max(np.abs(arr[:, :10] / gold[:, :10] - 1)) < 1e-9
+    assert os.path.exists(os.path.join(d2, "redTime_M002.dat"))
+    # sharding a manifest over processes: first/stride
+    os.remove(os.path.join(d1, "redTime_M001.dat"))
+    p = subprocess.run([exe, str(tmp_path / "manifest.txt"), "1", "2"], stdout=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0 and "1 models" in p.stdout and not os.path.exists(os.path.join(d1, "redTime_M001.dat"))
