@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--nk", type=int, default=128, help="output wavenumbers (the headline metric is nk=128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--print-all", action="store_true",
+                    help="PRINTA = PRINTI = PRINTQ = PRINTBIAS = 1: 84 columns per row (BASELINE configs[3])")
     ap.add_argument("--full-beta", action="store_true",
                     help="upload the full Beta_P(a,k) tables (default: the host pre-reduces them to what the run "
                          "consumes, rtrg_config.reduce_beta = 1)")
@@ -259,7 +261,8 @@ def run_b200(a, rank, world, local_rank):
     outputs_per_step = B * n_out
 
     reduce_beta = 0 if a.full_beta else 1
-    h = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta)
+    extra = dict(print_A=1, print_I=1, print_Q=1, print_bias=1) if a.print_all else {}
+    h = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta, **extra)
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -347,7 +350,7 @@ def run_b200(a, rank, world, local_rank):
         # outputs/s), so multi-rank runs report the serial number.
         t_pipe = None
         if world == 1:
-            h2 = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta)
+            h2 = rt.RedTimeB200(device=local_rank, nk=a.nk, reduce_beta=reduce_beta, **extra)
             hs = [h, h2]
             for hh in hs:                      # warm both handles' arenas
                 hh.clear()
@@ -424,7 +427,7 @@ def run_b200(a, rank, world, local_rank):
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "cosmologies_per_gpu": B, "redshifts": n_out, "nk": a.nk,
-                       "mode": a.mode, "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2"
+                       "mode": a.mode, "columns": 84 if a.print_all else 17, "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2"
                        % (sum(c["Tc_b"].nbytes * 2 for c in cosmos) / 1e9)},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernel_ms_in_timed_region": kernels}
