@@ -209,6 +209,9 @@ int rtrg_table_T(int nk, double kmin, double kmax, int n, double *T, double *kfa
 int rtrg_table_G(int nk, double kmin, double kmax, int n, double *G);
 /* windows WP[np], WC[np] */
 int rtrg_table_windows(int nk, double kmin, double kmax, double *WP, double *WC);
+/* Pab stencil on the padded grid (replaces Pab(), src/redTime.cc:181-232):
+   ln P(k_pad[ip]) = sum_j w[4 ip + j] lnP[n0[ip] + j] + (n_s - 3) dx[ip];  n0[np], w[4 np], dx[np] */
+int rtrg_table_extrap(int nk, double kmin, double kmax, int *n0, double *w, double *dx);
 /* assembly terms: returns count; arrays may be NULL to query the count */
 int rtrg_assembly_terms(int *row, int *src, int *index, int *kpow, double *coef, int cap);
 

@@ -97,6 +97,7 @@ def load_library():
     lib.rtrg_table_T.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp]
     lib.rtrg_table_G.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp]
     lib.rtrg_table_windows.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp]
+    lib.rtrg_table_extrap.argtypes = [C.c_int, C.c_double, C.c_double, _ip, _dp, _dp]
     lib.rtrg_assembly_terms.argtypes = [_ip, _ip, _ip, _ip, _dp, C.c_int]
     lib.rtrg_read_run_dir.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.rtrg_read_run_dirs.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
@@ -151,6 +152,14 @@ def table_windows(nk=128, kmin=1e-3, kmax=1.0):
     WP, WC = np.zeros(4 * nk), np.zeros(4 * nk)
     _check(lib.rtrg_table_windows(nk, kmin, kmax, _P(WP), _P(WC)))
     return WP, WC
+
+
+def table_extrap(nk=128, kmin=1e-3, kmax=1.0):
+    """Pab stencil on the padded grid: (n0[np], w[np,4], dx[np]); see rtrg_table_extrap."""
+    lib = load_library()
+    n0, w, dx = np.zeros(4 * nk, np.int32), np.zeros(16 * nk), np.zeros(4 * nk)
+    _check(lib.rtrg_table_extrap(nk, kmin, kmax, n0.ctypes.data_as(_ip), _P(w), _P(dx)))
+    return n0, w.reshape(4 * nk, 4), dx
 
 
 def assembly_terms():

@@ -436,39 +436,12 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     for (double &k : h->slot_k) k = std::min(std::max(k, cfg->beta_kmin), cfg->beta_kmax);
   }
   // --- Pab stencil for every padded sample (rt:181-232, itp:68-78)
-  std::vector<int> ex_n0(np);
-  std::vector<double> ex_w((size_t)4 * np, 0.0), ex_dx(np, 0.0);
+  std::vector<int> ex_n0;
+  std::vector<double> ex_w, ex_dx;
+  build_extrap_stencil(g, ex_n0, ex_w, ex_dx);
   for (int ip = 0; ip < np; ip++) {
     WP[ip] = window_P(g, ip);
-    const double k = std::exp(g.lnk_pad_min + g.dlnk * ip), lnk = std::log(k);
-    kpad[ip] = k;
-    const int nguess = (int)((lnk - lnkArr[0]) / g.dlnk);
-    int n = (nguess > 2 ? nguess - 2 : 0);
-    if (n > nk - 1) n = nk - 1;
-    while (n < nk - 1 && lnkArr[n + 1] < lnk) n++;
-    int type = 0;
-    if (n == 0) type = -1;
-    if (n == nk - 2) type = 1;
-    if (n >= nk - 1 || lnk > lnkArr[nk - 1]) type = 2;
-    double *w = &ex_w[(size_t)4 * ip];
-    if (type == 0) {
-      const double *p = &lnkArr[n - 1];
-      ex_n0[ip] = n - 1;
-      w[0] = (lnk - p[1]) * (lnk - p[2]) * (lnk - p[3]) / (p[0] - p[1]) / (p[0] - p[2]) / (p[0] - p[3]);
-      w[1] = (lnk - p[0]) * (lnk - p[2]) * (lnk - p[3]) / (p[1] - p[0]) / (p[1] - p[2]) / (p[1] - p[3]);
-      w[2] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[3]) / (p[2] - p[0]) / (p[2] - p[1]) / (p[2] - p[3]);
-      w[3] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[2]) / (p[3] - p[0]) / (p[3] - p[1]) / (p[3] - p[2]);
-    } else if (type == 2) {
-      ex_n0[ip] = nk - 4;
-      w[3] = 1.0;
-      ex_dx[ip] = lnk - lnkArr[nk - 1];
-    } else {
-      const int n0 = std::min(n, nk - 4);
-      ex_n0[ip] = n0;
-      const double t = (lnk - lnkArr[n]) / (lnkArr[n + 1] - lnkArr[n]);
-      w[n - n0] = 1.0 - t;
-      w[n + 1 - n0] = t;
-    }
+    kpad[ip] = std::exp(g.lnk_pad_min + g.dlnk * ip);
   }
   // --- assembly table sorted by output row.  Kernels with alpha = beta are symmetric,
   // T_n[u][v] = T_n[v][u], so J_n(ab,cd) = J_n(cd,ab): terms are redirected to the pair with

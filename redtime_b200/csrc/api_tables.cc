@@ -54,6 +54,18 @@ int rtrg_table_windows(int nk, double kmin, double kmax, double *WP, double *WC)
   return RTRG_OK;
 }
 
+int rtrg_table_extrap(int nk, double kmin, double kmax, int *n0, double *w, double *dx) {
+  if (nk < 16 || (nk % 16) != 0) return RTRG_EINVAL;
+  GridSpec g = make_grid(nk, kmin, kmax);
+  std::vector<int> vn0;
+  std::vector<double> vw, vdx;
+  build_extrap_stencil(g, vn0, vw, vdx);
+  if (n0) std::memcpy(n0, vn0.data(), vn0.size() * sizeof(int));
+  if (w) std::memcpy(w, vw.data(), vw.size() * sizeof(double));
+  if (dx) std::memcpy(dx, vdx.data(), vdx.size() * sizeof(double));
+  return RTRG_OK;
+}
+
 int rtrg_assembly_terms(int *row, int *src, int *index, int *kpow, double *coef, int cap) {
   const std::vector<AsmTerm> &t = assembly_terms();
   const int n = (int)t.size();

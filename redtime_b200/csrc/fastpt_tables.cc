@@ -2,6 +2,7 @@
 // Everything here runs once per (nk, kmin, kmax) grid at rtrg_create() time.
 #include "fastpt_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -309,6 +310,47 @@ void build_G(const GridSpec &g, int n, std::vector<double> &G) {
     } else {
       const double si = g.dlnk * d, r = std::exp(-si), r2 = r * r, r3 = r * r2;
       G[d + np - 1] = Zreg(zi, r) * r3;
+    }
+  }
+}
+
+void build_extrap_stencil(const GridSpec &g, std::vector<int> &ex_n0, std::vector<double> &ex_w,
+                          std::vector<double> &ex_dx) {
+  const int nk = g.nk, np = g.np;
+  std::vector<double> lnkArr(nk);
+  const double lnkmin = std::log(g.kmin);
+  for (int i = 0; i < nk; i++) lnkArr[i] = lnkmin + g.dlnk * i;  // rt:1559-1562
+  ex_n0.assign(np, 0);
+  ex_w.assign((size_t)4 * np, 0.0);
+  ex_dx.assign(np, 0.0);
+  for (int ip = 0; ip < np; ip++) {
+    const double k = std::exp(g.lnk_pad_min + g.dlnk * ip), lnk = std::log(k);
+    const int nguess = (int)((lnk - lnkArr[0]) / g.dlnk);
+    int n = (nguess > 2 ? nguess - 2 : 0);
+    if (n > nk - 1) n = nk - 1;
+    while (n < nk - 1 && lnkArr[n + 1] < lnk) n++;
+    int type = 0;
+    if (n == 0) type = -1;
+    if (n == nk - 2) type = 1;
+    if (n >= nk - 1 || lnk > lnkArr[nk - 1]) type = 2;
+    double *w = &ex_w[(size_t)4 * ip];
+    if (type == 0) {
+      const double *p = &lnkArr[n - 1];
+      ex_n0[ip] = n - 1;
+      w[0] = (lnk - p[1]) * (lnk - p[2]) * (lnk - p[3]) / (p[0] - p[1]) / (p[0] - p[2]) / (p[0] - p[3]);
+      w[1] = (lnk - p[0]) * (lnk - p[2]) * (lnk - p[3]) / (p[1] - p[0]) / (p[1] - p[2]) / (p[1] - p[3]);
+      w[2] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[3]) / (p[2] - p[0]) / (p[2] - p[1]) / (p[2] - p[3]);
+      w[3] = (lnk - p[0]) * (lnk - p[1]) * (lnk - p[2]) / (p[3] - p[0]) / (p[3] - p[1]) / (p[3] - p[2]);
+    } else if (type == 2) {
+      ex_n0[ip] = nk - 4;
+      w[3] = 1.0;
+      ex_dx[ip] = lnk - lnkArr[nk - 1];
+    } else {
+      const int n0 = std::min(n, nk - 4);
+      ex_n0[ip] = n0;
+      const double t = (lnk - lnkArr[n]) / (lnkArr[n + 1] - lnkArr[n]);
+      w[n - n0] = 1.0 - t;
+      w[n + 1 - n0] = t;
     }
   }
 }

@@ -33,6 +33,14 @@ GridSpec make_grid(int nk, double kmin, double kmax);
 double window_P(const GridSpec &g, int ipad);
 double window_C(const GridSpec &g, int m);
 
+// Pab on the padded grid (rt:181-232 with the tabulated-function rules itp:68-78) as a 4-point
+// stencil per padded sample ip:
+//   ln P_ab(k_pad[ip]) = sum_{j<4} w[4 ip + j] lnP_ab[n0[ip] + j] + (n_s - 3) dx[ip]
+// Inside the grid it is the 4-point Lagrange interpolant (the first and last interval fall back
+// to the linear one), above kmax the power-law tail k^(n_s-3) anchored at the last sample.
+void build_extrap_stencil(const GridSpec &g, std::vector<int> &n0, std::vector<double> &w,
+                          std::vector<double> &dx);
+
 // The 14 bilinear kernels: 0..6 = J (alpha,-alpha,ell) (redTime.cc:731-732; n=1 regularised),
 //                          7..13 = Jn0 (redTime.cc:734-736)
 #ifndef RTRG_NKERN_DEFINED

@@ -96,3 +96,24 @@ def test_assembly_table_reproduces_reference_outputs(stage_golden_1loop):
     for j in range(64):
         if j not in used:
             assert not A[j].any()
+
+
+def test_extrap_stencil_reproduces_Pab_times_window(stage_golden_1loop, tmp_path):
+    """Pab(a,b,k_pad,y) * WP (rt:181-232, 772-778) as the 4-point stencil the device kernel
+    k_extrap applies: ln P = sum_j w_j lnP[n0+j] + (n_s-3) dx, on the oracle's states y0 / yp."""
+    from conftest import make_example1_dir
+    ns = rt.read_run_dir(make_example1_dir(str(tmp_path / "M")))["params"][0]
+    g = stage_golden_1loop
+    n0, w, dx = rt.table_extrap(NK)
+    WP, _ = rt.table_windows(NK)
+    assert n0.min() == 0 and n0.max() == NK - 4
+    assert np.allclose(w.sum(1), 1.0, rtol=0, atol=1e-12)     # interpolation weights
+    assert np.all(dx[:192 + NK] == 0) and np.all(dx[192 + NK:] > 0)  # power-law tail above kmax only
+    for tag in ("y0", "yp"):
+        y = g[tag][:3 * NK].reshape(3, NK)
+        lnP = (w[None] * y[:, n0[:, None] + np.arange(4)[None]]).sum(-1) + (ns - 3) * dx[None]
+        P = np.where(WP > 0, np.exp(lnP) * WP, 0.0)
+        ref = g["P3_" + tag]
+        assert np.all((P == 0) == (ref == 0))
+        m = ref != 0
+        assert np.max(np.abs(P[m] / ref[m] - 1)) < 1e-13
