@@ -348,12 +348,18 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   h->grid = make_grid(cfg->nk, cfg->kmin, cfg->kmax);
   std::memset(&h->S, 0, sizeof h->S);
   std::memset(&h->tb, 0, sizeof h->tb);
-  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
+  {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      rtrg_destroy(h);
+      return fail(RTRG_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+  }
   h->stream = h->own_stream;
   if (linear_upload_constants() != 0) {
-    delete h;
+    rtrg_destroy(h);
     return fail(RTRG_ECUDA, "constant upload failed");
   }
   integrals_configure();
@@ -1194,7 +1200,7 @@ int rtrg_fetch_outputs(rtrg_handle *h, const double **out, size_t *out_len, cons
 }
 
 int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
-  if (!h || i < 0 || (size_t)(4 * i + 3) >= h->counters.size()) return RTRG_EINVAL;
+  if (!h || !counters || i < 0 || (size_t)(4 * i + 3) >= h->counters.size()) return RTRG_EINVAL;
   for (int j = 0; j < 4; j++) counters[j] = h->counters[4 * i + j];
   return RTRG_OK;
 }
