@@ -32,6 +32,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the harness keeps the weight-table cache inside the repository (the library default is ~/.cache)
+os.environ.setdefault("RTRG_CACHE_DIR", os.path.join(ROOT, ".rtrg_cache"))
 
 METRIC = "cosmology*redshift outputs/sec at nk=128"
 UNIT = "outputs/s"

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 ORACLE_REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, ROOT)
+# the harness keeps the weight-table cache inside the repository (the library default is ~/.cache)
+os.environ.setdefault("RTRG_CACHE_DIR", os.path.join(ROOT, ".rtrg_cache"))
 
 
 def pytest_configure(config):
