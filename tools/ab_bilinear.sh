@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of the bilinear kernel variants (RTRG_BIL = ldg | tma3 | tma2 | tma3s2): timing of the
+# A/B harness for bilinear kernel variants selected by the environment variable RTRG_BIL (the
+# round-1 variants tma3 / tma3s2 / ldg384 were measured and dropped, see
+# profiles/r01_bilinear_experiments.txt; the shipped library ignores the variable): timing of the
 # integral evaluation and an md5 of a mixed 7-cosmology run (the variants must agree bit for bit).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
