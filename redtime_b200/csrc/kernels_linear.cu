@@ -111,6 +111,10 @@ struct GrowthRhsDev {
   int n_z;
   bool has_beta;
   mutable int n_last;
+  // the table values around interval n_last, re-read from global memory only when the interval
+  // changes (the 13 stage abscissae of an attempt almost always share it)
+  mutable int n_cached;
+  mutable double bc[4];
   __device__ __forceinline__ double beta(double a) const {
     if (!has_beta) return 0.0;
     if (a > 1.0) a = 1.0;
@@ -120,18 +124,31 @@ struct GrowthRhsDev {
       n = tab_find(s_a, X, a);
       n_last = n;
     }
-    if (n > 0 && n < X - 2) {
+    const bool cubic = n > 0 && n < X - 2;
+    if (n != n_cached) {
+      n_cached = n;
+      if (cubic) {
+        bc[0] = brow[(n - 1) * bstride], bc[1] = brow[n * bstride];
+        bc[2] = brow[(n + 1) * bstride], bc[3] = brow[(n + 2) * bstride];
+      } else {
+        bc[1] = brow[n * bstride], bc[2] = brow[(n + 1) * bstride];
+      }
+    }
+    if (cubic) {
       const double d0 = a - s_a[n - 1], d1 = a - s_a[n], d2 = a - s_a[n + 1], d3 = a - s_a[n + 2];
       const double *iv = s_inv + 4 * n;
-      return d1 * d2 * d3 * iv[0] * brow[(n - 1) * bstride] + d0 * d2 * d3 * iv[1] * brow[n * bstride] +
-             d0 * d1 * d3 * iv[2] * brow[(n + 1) * bstride] + d0 * d1 * d2 * iv[3] * brow[(n + 2) * bstride];
+      return d1 * d2 * d3 * iv[0] * bc[0] + d0 * d2 * d3 * iv[1] * bc[1] + d0 * d1 * d3 * iv[2] * bc[2] +
+             d0 * d1 * d2 * iv[3] * bc[3];
     }
-    const double f0 = brow[n * bstride], f1 = brow[(n + 1) * bstride];
+    const double f0 = bc[1], f1 = bc[2];
     return f0 + (f1 - f0) * iv_lin(n) * (a - s_a[n]);
   }
   __device__ __forceinline__ double iv_lin(int n) const { return 1.0 / (s_a[n + 1] - s_a[n]); }
-  __device__ __forceinline__ void operator()(double a, const double y[2], double f[2]) const {
-    const BgStatic &s = bg;
+  // the part of the right-hand side that depends on a alone (hdr:151-160, 466-500)
+  struct Coef {
+    double F0, F1;
+  };
+  static __device__ __forceinline__ Coef coef(const BgStatic &s, double a) {
     const double a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a4 * a, ainv = 1.0 / a;
     const double E = exp(-3.0 * (1.0 + s.w0 + s.wa) * log(a) - 3.0 * s.wa * (1.0 - a));
     const double dEda = 3.0 * E * (s.wa - (1.0 + s.w0 + s.wa) * ainv);
@@ -139,13 +156,129 @@ struct GrowthRhsDev {
     const double H2 = (s.Om - s.On) * (1.0 + Y) / a3 + s.OL * E + s.Og / a4;
     const double dlnH = 0.5 * a / H2 *
                         (s.fc * s.Om * (-3.0 * (1.0 + Y) + a * dYda) / a4 + s.OL * dEda - 4.0 * s.Og / a5);
-    const double F0 = 1.5 * s.Om / (a5 * H2);
-    const double F1 = (3.0 + dlnH) * ainv;
-    const double bt = (a < 1e-3) ? s.fn : beta(a);
+    Coef c;
+    c.F0 = 1.5 * s.Om / (a5 * H2);
+    c.F1 = (3.0 + dlnH) * ainv;
+    return c;
+  }
+  __device__ __forceinline__ void apply(double a, const Coef &c, const double y[2], double f[2]) const {
+    const double bt = (a < 1e-3) ? bg.fn : beta(a);
     f[0] = y[1];
-    f[1] = -F1 * y[1] + F0 * (s.fc + bt) * y[0];
+    f[1] = -c.F1 * y[1] + c.F0 * (bg.fc + bt) * y[0];
+  }
+  __device__ __forceinline__ void operator()(double a, const double y[2], double f[2]) const {
+    apply(a, coef(bg, a), y, f);
   }
 };
+
+// Warp-cooperative form of growth_integrate (rtrg_math.h; same arithmetic per lane, bit for bit).
+// The lanes of a warp integrate the wavenumbers of ONE cosmology, and almost always in lock
+// step: every leg restarts from h = 1e-6 a (hdr:170-190), grows by the capped factor 5 and ends
+// on the clamped final step, so (t0, h0) of an attempt are the same in all lanes.  Then the 13
+// stage abscissae are the same too, and F0(a), F1(a) -- a log, an exp and six divisions, ~85 % of
+// the dependent chain of a stage -- are evaluated once per attempt by 13 lanes in parallel and
+// passed through shared memory, instead of 13 times in sequence by every lane.  Attempts in
+// which the lanes disagree (a rejection at one wavenumber) fall back to per-lane evaluation.
+__device__ void growth_integrate_coop(const GrowthRhsDev &g, double a_begin, double a_end, double y[2],
+                                      bool valid, double *s_cf) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const double(*A)[12] = c_pd.A;
+  const double *C = c_pd.C, *B8 = c_pd.B8, *B7 = c_pd.B7;
+  double t = a_begin;
+  const double t1 = a_end;
+  double h = 1e-6 * t;
+  int attempts = 0;
+  bool alive = valid, retry = false;
+  double t0 = t, dt = 0.0, h0 = h, y0[2] = {y[0], y[1]};
+  double k[13][2];
+  for (;;) {
+    if (alive && !retry && !((t1 - t) * h > 0)) alive = false;
+    const unsigned ball = __ballot_sync(FULL, alive);
+    if (!ball) break;
+    if (alive && !retry) {  // --- gsl_odeiv_evolve_apply starts
+      t0 = t, dt = t1 - t0, h0 = h;
+      y0[0] = y[0], y0[1] = y[1];
+    }
+    bool final_step = false;
+    if (alive && ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt))) {
+      h0 = dt;
+      final_step = true;
+    }
+    const int leader = __ffs(ball) - 1;
+    const double lt = __shfl_sync(FULL, t0, leader), lh = __shfl_sync(FULL, h0, leader);
+    const bool coop = __all_sync(FULL, !alive || (t0 == lt && h0 == lh));
+    if (coop) {
+      if (lane < 13) {
+        const GrowthRhsDev::Coef c = GrowthRhsDev::coef(g.bg, lane == 0 ? lt : lt + C[lane] * lh);
+        s_cf[2 * lane] = c.F0;
+        s_cf[2 * lane + 1] = c.F1;
+      }
+      __syncwarp();
+    }
+    if (alive) {
+      if (!retry) {
+        GrowthRhsDev::Coef c;
+        if (coop) c.F0 = s_cf[0], c.F1 = s_cf[1];
+        else c = GrowthRhsDev::coef(g.bg, t0);
+        g.apply(t0, c, y0, k[0]);
+      }
+      for (int s = 1; s < 13; s++) {
+        double acc0 = 0, acc1 = 0;
+        for (int j = 0; j < s; j++) {
+          const double a_sj = A[s][j];
+          if (a_sj != 0.0) {
+            acc0 += a_sj * k[j][0];
+            acc1 += a_sj * k[j][1];
+          }
+        }
+        const double yt[2] = {y0[0] + h0 * acc0, y0[1] + h0 * acc1};
+        const double as = t0 + C[s] * h0;
+        GrowthRhsDev::Coef c;
+        if (coop) c.F0 = s_cf[2 * s], c.F1 = s_cf[2 * s + 1];
+        else c = GrowthRhsDev::coef(g.bg, as);
+        g.apply(as, c, yt, k[s]);
+      }
+      double s8[2] = {0, 0}, s7[2] = {0, 0};
+      for (int j = 0; j < 13; j++) {
+        if (B8[j] != 0.0) {
+          s8[0] += B8[j] * k[j][0];
+          s8[1] += B8[j] * k[j][1];
+        }
+        if (B7[j] != 0.0) {
+          s7[0] += B7[j] * k[j][0];
+          s7[1] += B7[j] * k[j][1];
+        }
+      }
+      const double yn[2] = {y0[0] + h0 * s8[0], y0[1] + h0 * s8[1]};
+      const double ye[2] = {h0 * (s7[0] - s8[0]), h0 * (s7[1] - s8[1])};
+      attempts++;
+      const double tn = final_step ? t1 : t0 + h0;
+      double rmax = DBL_MIN;  // control_y_new(0, 1e-6), order 8
+      for (int i = 0; i < 2; i++) {
+        const double D0 = 1e-6 * fabs(yn[i]) + 0.0;
+        const double r = fabs(ye[i]) / fabs(D0);
+        if (r > rmax) rmax = r;
+      }
+      const double h_old = h0;
+      const int adj = gsl_hadjust(rmax, 8, &h0);
+      retry = false;
+      if (adj == -1) {
+        const double t_next = tn + h0;
+        if (fabs(h0) < fabs(h_old) && t_next != tn) retry = true;  // reject, retry smaller
+        else h0 = h_old;
+      }
+      if (!retry) {
+        y[0] = yn[0];
+        y[1] = yn[1];
+        t = tn;
+        h = h0;
+        if (attempts > 2000000) alive = false;
+      }
+    }
+    __syncwarp();  // s_cf is rewritten by the next attempt
+  }
+}
 
 __global__ void __launch_bounds__(64) k_growth_ode(Batch S) {
   const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,27 +298,33 @@ __global__ void __launch_bounds__(64) k_growth_ode(Batch S) {
     }
   }
   __syncthreads();
-  if (j > S.n_lnk) return;
+  const bool valid = j <= S.n_lnk;  // lanes beyond the last wavenumber still help with the coefficients
+  double *s_cf = s_inv + 4 * S.n_zmax + (threadIdx.x >> 5) * 26;
   GrowthRhsDev g;
   g.bg = bg_static(c);
-  g.brow = S.bred + (long long)b * S.n_zmax * S.nkk + (S.nk + j);
+  g.brow = S.bred + (long long)b * S.n_zmax * S.nkk + (S.nk + (valid ? j : 0));
   g.bstride = S.nkk;
   g.s_a = s_a;
   g.s_inv = s_inv;
   g.n_z = c.n_z;
   g.has_beta = has_beta;
   g.n_last = 0;
+  g.n_cached = -1;
   const int nj = S.n_lnk + 1;
   double *G = S.G + (long long)b * (S.n_lna + 1) * nj, *dD = S.dD + (long long)b * (S.n_lna + 1) * nj;
   double y[2] = {1.0, 1.0 / S.a_early};  // hdr:697-698
-  growth_integrate(c_pd, g, S.a_early, GROWTH_A_MIN, y);
-  G[j] = y[0] / GROWTH_A_MIN;
-  dD[j] = y[1];
+  growth_integrate_coop(g, S.a_early, GROWTH_A_MIN, y, valid, s_cf);
+  if (valid) {
+    G[j] = y[0] / GROWTH_A_MIN;
+    dD[j] = y[1];
+  }
   for (int i = 1; i <= S.n_lna; i++) {
     const double a1 = exp(S.lna[i]);
-    growth_integrate(c_pd, g, exp(S.lna[i - 1]), a1, y);
-    G[(long long)i * nj + j] = y[0] / a1;
-    dD[(long long)i * nj + j] = y[1];
+    growth_integrate_coop(g, exp(S.lna[i - 1]), a1, y, valid, s_cf);
+    if (valid) {
+      G[(long long)i * nj + j] = y[0] / a1;
+      dD[(long long)i * nj + j] = y[1];
+    }
   }
 }
 
@@ -381,7 +520,7 @@ int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Pro
   k_beta_reduce<<<dim3((S.nkk + 127) / 128, B), 128, 0, st>>>(S, kgrid), n++;
   RT_TOC(prof, st);
   RT_TIC(prof, PC_GROWTH_ODE, st);
-  k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, (size_t)5 * S.n_zmax * sizeof(double), st>>>(S), n++;
+  k_growth_ode<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, ((size_t)5 * S.n_zmax + 2 * 26) * sizeof(double), st>>>(S), n++;
   RT_TOC(prof, st);
   RT_TIC(prof, PC_GROWTH_TABS, st);
   k_growth_norm<<<dim3((S.n_lnk + 1 + 63) / 64, B), 64, 0, st>>>(S), n++;

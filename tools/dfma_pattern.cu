@@ -27,6 +27,17 @@ __global__ void __launch_bounds__(352, WMODE == 1 ? 1 : 2) k_pat(const double *_
     for (int q = 0; q < 3; q++) acc[r][q] = 0.0;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    if (WMODE == 3) {  // all three slots' windows at the top of the chunk: 96 registers' worth
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const double2 *wp = reinterpret_cast<const double2 *>(&s_w[q][(it & 31) * 8]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const double2 v = wp[i];
+          w[q][2 * i] = v.x, w[q][2 * i + 1] = v.y;
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 3; q++) {
       if (WMODE == 2) {
@@ -136,5 +147,7 @@ int main() {
   RUN(2, 1, "row-major, windows in vector registers");
   RUN(0, 2, "lag-major, windows from LDS.128 per chunk");
   RUN(1, 2, "window-major, windows from LDS.128 per chunk");
+  RUN(0, 3, "lag-major, all windows loaded at chunk top");
+  RUN(1, 3, "window-major, all windows loaded at chunk top");
   return 0;
 }
