@@ -41,8 +41,10 @@ void launch_hook_beta(const Batch &S, int b, double a, const double *k, int n, d
 void launch_hook_plin(const Batch &S, int b, int which, double z, const double *k, int n, double *P,
                       cudaStream_t st);
 // kernels_ode.cu
+int ode_configure();
 void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *dyv, int stage,
                 const int *mask, cudaStream_t st);
+void launch_attempt_local(const Batch &S, const double *kgrid, const int *mask, cudaStream_t st);
 void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st);
 void launch_final(const Batch &S, const int *mask, cudaStream_t st);
 void launch_ctrl_begin(const Batch &S, cudaStream_t st);
@@ -149,7 +151,7 @@ struct rtrg_handle {
   std::vector<long long> out_off, counters, matvecs;
   std::vector<int> ncols;
   size_t out_total = 0;
-  bool any_full = false, any_1loop = false, any_pr = false;
+  bool any_full = false, any_1loop = false, any_pr = false, any_local = false;
   double *d_yinit = nullptr, *d_raw = nullptr, *d_scratch = nullptr;
   int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
   size_t scratch_len = 0;
@@ -363,6 +365,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     return fail(RTRG_ECUDA, "constant upload failed");
   }
   integrals_configure();
+  ode_configure();
 
   const GridSpec &g = h->grid;
   const int nk = g.nk, np = g.np;
@@ -816,7 +819,7 @@ int rtrg_prepare(rtrg_handle *h) {
   h->ncols.assign(B, 0);
   size_t off = 0;
   int n_zmax = 2, max_rows = 1;
-  h->any_full = h->any_1loop = h->any_pr = false;
+  h->any_full = h->any_1loop = h->any_pr = h->any_local = false;
   for (int b = 0; b < B; b++) {
     const HostCosmo &hc = h->cos[b];
     const Cosmo &c = hc.c;
@@ -845,6 +848,7 @@ int rtrg_prepare(rtrg_handle *h) {
     h->out_off[b] = (long long)off;
     off += (size_t)c.n_out * nk * h->ncols[b];
     if (c.sw_nl && !c.sw_1l) h->any_full = true;
+    else h->any_local = true;
     if (c.sw_nl && c.sw_1l) h->any_1loop = true;
     if (c.sw_pr) h->any_pr = true;
     const int st_keep = cs[b].status;
@@ -914,6 +918,7 @@ int rtrg_prepare(rtrg_handle *h) {
     S.m_full_step = A.take<int>(B);
     S.m_full_acc = A.take<int>(B);
     S.m_out_int = A.take<int>(B);
+    S.m_loc_step = A.take<int>(B);
     S.counters = A.take<long long>((size_t)4 * B);
     S.matvecs = A.take<long long>(B);
     S.act = A.take<int>(B);
@@ -1060,8 +1065,8 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
     h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof);
+    ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, h->d_minit, st));
   }
-  ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, nullptr, st));
 
   long long rounds = 0;
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
@@ -1074,21 +1079,26 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     if (h->any_1loop && grp_out(h))
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, grp_out(h), 0, st, h->prof);
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
-    for (int s = 1; s < RK_STAGES; s++) {
-      ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.flag_step, st));
-      if (h->any_full) XCH(gather_lnP(S.ytmp));
-      if (h->any_full)
+    // cosmologies without integrals inside the RHS (1-loop, linear): the whole attempt in one kernel
+    if (h->any_local) ODE_LAUNCH(PC_ATTEMPT, launch_attempt_local(S, h->d_kgrid, S.m_loc_step, st));
+    // full Time-RG: the stages are separated by integral evaluations (and the k-shard exchange)
+    if (h->any_full) {
+      for (int s = 1; s < RK_STAGES; s++) {
+        ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.m_full_step, st));
+        XCH(gather_lnP(S.ytmp));
         h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, grp_rhs(h), 0, st, h->prof);
-      ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.flag_step, st));
+        ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.m_full_step, st));
+      }
+      ODE_LAUNCH(PC_FINAL, launch_final(S, S.m_full_step, st));
     }
-    ODE_LAUNCH(PC_FINAL, launch_final(S, S.flag_step, st));
     if (sharded) XCH(h->xch->allreduce_max_u64(S.rmax_bits, B, st, &xerr));
     ODE_LAUNCH(PC_CTRL, launch_ctrl_end(S, h->cfg.max_attempts, st));
     ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
     XCH(gather_lnP(S.y));  // keep ln P of the accepted state complete on every rank
-    if (h->any_full)
+    if (h->any_full) {  // dydt_in of the next attempt
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof);
-    ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.flag_acc, st));
+      ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.m_full_acc, st));
+    }
     return RTRG_OK;
   };
   // no graph while per-kernel timing is on (events between the nodes), for the host-driven
@@ -1265,7 +1275,7 @@ int rtrg_set_profiling(rtrg_handle *h, int on) {
 int rtrg_profile_categories(void) { return PC_NCAT; }
 const char *rtrg_profile_name(int cat) {
   static const char *names[PC_NCAT] = {"k_extrap", "k_bilinear", "k_jlo", "k_pz", "k_assemble", "k_rhs",
-                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_prep_inputs", "k_beta_reduce",
+                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_attempt_local", "k_prep_inputs", "k_beta_reduce",
                                        "k_growth_ode", "k_growth_tabs", "k_qag", "k_init_state"};
   return (cat >= 0 && cat < PC_NCAT) ? names[cat] : "";
 }

@@ -42,6 +42,49 @@ struct RhsShared {
   RowX xb, xg;
   int beta_zero, beta_bad, growth_ok;
 };
+// time-only part of one right-hand-side evaluation at eta (one thread per block)
+__device__ __forceinline__ void rhs_time_setup(const Batch &S, const Cosmo &c, double eta, RhsShared &sh) {
+  const double A = c.a_in * exp(eta);  // rt:1430
+  sh.eta = eta;
+  sh.A = A;
+  sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
+  sh.Om11 = 3.0 + bg_dlnH(c, A);
+  // Beta_P(A, k): 0 without massive neutrinos, abort in the reference for A > 1.001 (hdr:523-531)
+  sh.beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10);
+  sh.beta_bad = (!sh.beta_zero && A > 1.001);
+  if (!sh.beta_zero && !sh.beta_bad) sh.xb = tab_row_x_prepare(S.in + c.offA, c.n_z, A > 1.0 ? 1.0 : A);
+  // growth look-up of the 1-loop rescaling (rt:1316-1337)
+  sh.z = exp(-eta) * (1.0 + c.z_in) - 1;
+  sh.a = 1.0 / (sh.z + 1.0);
+  sh.growth_ok = !(sh.a > GROWTH_A_MAX || sh.a < GROWTH_A_MIN);
+  if (sh.growth_ok) sh.xg = tab_row_x_prepare(S.lna, S.n_lna + 1, log(sh.a));
+  sh.pre4 = exp(-4.0 * eta);
+}
+// row-dependent coefficients of that evaluation: Omega_10, and in 1-loop mode the rescaling of the
+// z1l cache, sources x (D/D_z1l)^4 e^{-4 eta} f^n (rt:1316-1337): *pre and f = *fz
+__device__ __forceinline__ void rhs_row_coeffs(const Batch &S, const Cosmo &c, int b, int i, const RhsShared &sh,
+                                               double *Om10, double *pre, double *fz) {
+  const int nk = S.nk;
+  double beta = 0.0;
+  if (sh.beta_bad) beta = NAN;
+  else if (!sh.beta_zero) beta = tab_row_x_apply(sh.xb, S.bred + (long long)b * S.n_zmax * S.nkk + i, S.nkk);
+  *Om10 = -1.5 * c.Om * (c.fcb + beta) / sh.om10_den;
+  *pre = 1.0;
+  *fz = 1.0;
+  if (c.sw_nl && c.sw_1l) {
+    double D = NAN, dD = NAN;
+    if (sh.growth_ok) {
+      const long long o = (long long)b * (S.n_lna + 1) * nk + i;
+      const double D0 = S.D0row[(long long)b * nk + i];
+      D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
+      dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
+    }
+    *fz = dD / (D * (1.0 + sh.z));
+    const double rD = D / S.D_z1l[(long long)b * nk + i];
+    *pre = (rD * rD) * (rD * rD) * sh.pre4;
+  }
+}
+
 __global__ void __launch_bounds__(128)
     k_rhs(Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv,
           double *__restrict__ dyv, int stage, const int *__restrict__ mask) {
@@ -50,50 +93,19 @@ __global__ void __launch_bounds__(128)
   const Cosmo &c = S.cosmo[b];
   const int nk = S.nk;
   __shared__ RhsShared sh;
-  if (threadIdx.x == 0) {
-    const double eta = (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b];
-    const double A = c.a_in * exp(eta);  // rt:1430
-    sh.eta = eta;
-    sh.A = A;
-    sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
-    sh.Om11 = 3.0 + bg_dlnH(c, A);
-    // Beta_P(A, k): 0 without massive neutrinos, abort in the reference for A > 1.001 (hdr:523-531)
-    sh.beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10);
-    sh.beta_bad = (!sh.beta_zero && A > 1.001);
-    if (!sh.beta_zero && !sh.beta_bad) sh.xb = tab_row_x_prepare(S.in + c.offA, c.n_z, A > 1.0 ? 1.0 : A);
-    // growth look-up of the 1-loop rescaling (rt:1316-1337)
-    sh.z = exp(-eta) * (1.0 + c.z_in) - 1;
-    sh.a = 1.0 / (sh.z + 1.0);
-    sh.growth_ok = !(sh.a > GROWTH_A_MAX || sh.a < GROWTH_A_MIN);
-    if (sh.growth_ok) sh.xg = tab_row_x_prepare(S.lna, S.n_lna + 1, log(sh.a));
-    sh.pre4 = exp(-4.0 * eta);
-  }
+  if (threadIdx.x == 0) rhs_time_setup(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
   __syncthreads();
   const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.k_hi) return;
   const double eta = sh.eta, eeta = exp(eta);
   const double k = kgrid[i];
-
-  double beta = 0.0;
-  if (sh.beta_bad) beta = NAN;
-  else if (!sh.beta_zero) beta = tab_row_x_apply(sh.xb, S.bred + (long long)b * S.n_zmax * S.nkk + i, S.nkk);
-  const double Om10 = -1.5 * c.Om * (c.fcb + beta) / sh.om10_den, Om11 = sh.Om11;
-
-  // 1-loop mode: the sources are the z1l cache rescaled by (D/D_z1l)^4 e^{-4 eta} f^n (rt:1316-1337)
   const int one_loop = c.sw_nl && c.sw_1l;
   const int evolve_Q = (S.print_Q || c.sw_pr);
-  double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pre = 1.0;
+  double Om10, pre, fz;
+  rhs_row_coeffs(S, c, b, i, sh, &Om10, &pre, &fz);
+  const double Om11 = sh.Om11;
+  double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
   if (one_loop) {
-    double D = NAN, dD = NAN;
-    if (sh.growth_ok) {
-      const long long o = (long long)b * (S.n_lna + 1) * nk + i;
-      const double D0 = S.D0row[(long long)b * nk + i];
-      D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
-      dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
-    }
-    const double fz = dD / (D * (1.0 + sh.z));
-    const double rD = D / S.D_z1l[(long long)b * nk + i];
-    pre = (rD * rD) * (rD * rD) * sh.pre4;
 #pragma unroll
     for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
   }
@@ -133,6 +145,158 @@ __global__ void __launch_bounds__(128)
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) db[(long long)(j0 + j) * nk] = dQ[j];
+  }
+}
+
+// ---------------------------------------------------------------------------- k_attempt_local
+// One whole RKF45 attempt of the cosmologies whose right-hand side needs no new integrals (1-loop
+// and linear mode): there the 41 equations of a row split into four independent systems -- ln P
+// with I (17), and the three multipoles of Q (8 each) -- and no row talks to another one, so
+// the six stages, the combinations between them, the 5th-order solution and the error norm are
+// done by one thread per (row, system) with the stage derivatives kept in shared memory.  Same
+// formulas, in the same order, as k_rhs / k_combine / k_final, which remain the path of the
+// full Time-RG cosmologies (their stages are separated by integral evaluations).  HBM traffic:
+// y and the sources in, ynew out = 960 B per row instead of ~17.6 KB through the kernel chain.
+enum { ATT_ROWS = 32 };
+template <int NC>
+__device__ __forceinline__ void att_combine(const double *s_k, int stage, int lane, double h, const double *y,
+                                            double *yt) {
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    double acc = 0.0;
+    for (int m = 0; m < stage; m++) {
+      const double a = RKF45::a(stage, m);
+      if (a != 0.0) acc += a * s_k[(m * NC + j) * ATT_ROWS + lane];
+    }
+    yt[j] = y[j] + h * acc;
+  }
+}
+template <int NC>
+__device__ __forceinline__ double att_final(const Batch &S, const double *s_k, int lane, double h, const double *y,
+                                            double *yn_out, long long stride) {
+  double r = 0.0;
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    double acc = 0.0, err = 0.0;
+#pragma unroll
+    for (int m = 0; m < RK_STAGES; m++) {
+      const double km = s_k[(m * NC + j) * ATT_ROWS + lane];
+      if (RKF45::b(m) != 0.0) acc += RKF45::b(m) * km;
+      if (RKF45::e(m) != 0.0) err += RKF45::e(m) * km;
+    }
+    const double yn = y[j] + h * acc, ye = h * err;
+    yn_out[(long long)j * stride] = yn;
+    const double D0 = S.eps_rel * fabs(yn) + S.eps_abs;
+    double rj = fabs(ye) / fabs(D0);
+    if (!(rj == rj)) rj = 0.0;  // GSL_MAX_DBL ignores NaN
+    r = fmax(r, rj);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(128)
+    k_attempt_local(Batch S, const double *__restrict__ kgrid, const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (!mask[b]) return;
+  const Cosmo &c = S.cosmo[b];
+  const int nk = S.nk, lane = threadIdx.x & 31, piece = threadIdx.x >> 5;
+  __shared__ RhsShared sh[RK_STAGES];
+  __shared__ double s_om10[RK_STAGES][ATT_ROWS], s_pre[RK_STAGES][ATT_ROWS], s_fz[RK_STAGES][ATT_ROWS];
+  __shared__ double s_r[4];
+  extern __shared__ double s_kall[];  // PI: [6][17][32]; Q_l: [6][8][32] each
+  const double h = S.h_try[b];
+  if (threadIdx.x < RK_STAGES)
+    rhs_time_setup(S, c, threadIdx.x == 0 ? S.t[b] : S.t[b] + RKF45::c(threadIdx.x) * h, sh[threadIdx.x]);
+  __syncthreads();
+  const int i0 = S.k_lo + blockIdx.x * ATT_ROWS;
+  for (int it = threadIdx.x; it < RK_STAGES * ATT_ROWS; it += blockDim.x) {
+    const int st = it / ATT_ROWS, r = it - st * ATT_ROWS;
+    if (i0 + r < S.k_hi) rhs_row_coeffs(S, c, b, i0 + r, sh[st], &s_om10[st][r], &s_pre[st][r], &s_fz[st][r]);
+  }
+  __syncthreads();
+  const int i = i0 + lane;
+  const int one_loop = c.sw_nl && c.sw_1l;
+  const int evolve_Q = (S.print_Q || c.sw_pr);
+  double r = 0.0;
+  if (i < S.k_hi) {
+    const double k = kgrid[i];
+    const double *s1 = (one_loop ? S.src_z1l : S.src) + (long long)b * N_SRC * nk + i;
+    const double *yb = S.y + (long long)b * N_U * nk + i;
+    double *yn = S.ynew + (long long)b * N_U * nk + i;
+    if (piece == 0) {
+      constexpr int NC = N_UP + N_UI;
+      double *s_k = s_kall;
+      double y[NC], A0[N_UI];
+#pragma unroll
+      for (int j = 0; j < NC; j++) y[j] = yb[(long long)j * nk];
+#pragma unroll
+      for (int j = 0; j < N_UI; j++) A0[j] = s1[(long long)j * nk];
+      for (int st = 0; st < RK_STAGES; st++) {
+        double yt[NC], dy[NC], A14[N_UI];
+        if (st == 0) {
+#pragma unroll
+          for (int j = 0; j < NC; j++) yt[j] = y[j];
+        } else {
+          att_combine<NC>(s_k, st, lane, h, y, yt);
+        }
+        const double pre = s_pre[st][lane], fz = s_fz[st][lane];
+        double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+        if (one_loop) {
+#pragma unroll
+          for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
+        }
+#pragma unroll
+        for (int j = 0; j < N_UI; j++)
+          A14[j] = !c.sw_nl ? 0.0 : one_loop ? pre * fp[a14_fpow(j)] * A0[j] : A0[j];
+        trg_rhs_PI(exp(sh[st].eta), k, s_om10[st][lane], sh[st].Om11, c.sw_nl, yt, A14, dy);
+#pragma unroll
+        for (int j = 0; j < NC; j++) s_k[(st * NC + j) * ATT_ROWS + lane] = dy[j];
+      }
+      r = att_final<NC>(S, s_k, lane, h, y, yn, nk);
+    } else {
+      constexpr int NC = 8;
+      const int l = piece - 1, j0 = N_UP + N_UI + 8 * l;
+      double *s_k = s_kall + RK_STAGES * (N_UP + N_UI) * ATT_ROWS + l * RK_STAGES * NC * ATT_ROWS;
+      double y[NC], R0[NC];
+      const bool on = c.sw_nl && evolve_Q;
+#pragma unroll
+      for (int j = 0; j < NC; j++) y[j] = yb[(long long)(j0 + j) * nk];
+#pragma unroll
+      for (int j = 0; j < NC; j++) R0[j] = on ? s1[(long long)(N_UI + 8 * l + j) * nk] : 0.0;
+      for (int st = 0; st < RK_STAGES; st++) {
+        double yt[NC], dQ[NC], R[NC];
+        if (st == 0) {
+#pragma unroll
+          for (int j = 0; j < NC; j++) yt[j] = y[j];
+        } else {
+          att_combine<NC>(s_k, st, lane, h, y, yt);
+        }
+        if (on) {
+          const double pre = s_pre[st][lane], fz = s_fz[st][lane];
+          double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+          if (one_loop) {
+#pragma unroll
+            for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
+          }
+#pragma unroll
+          for (int j = 0; j < NC; j++) R[j] = one_loop ? pre * fp[r24_fpow(8 * l + j)] * R0[j] : R0[j];
+          trg_rhs_Q(exp(sh[st].eta), s_om10[st][lane], sh[st].Om11, yt, R, dQ);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; j++) dQ[j] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) s_k[(st * NC + j) * ATT_ROWS + lane] = dQ[j];
+      }
+      r = att_final<NC>(S, s_k, lane, h, y, yn + (long long)j0 * nk, nk);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if (lane == 0) s_r[piece] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    r = fmax(fmax(s_r[0], s_r[1]), fmax(s_r[2], s_r[3]));
+    atomicMax(&S.rmax_bits[b], (unsigned long long)__double_as_longlong(r));
   }
 }
 
@@ -197,7 +361,7 @@ __global__ void k_ctrl_begin(Batch S) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= S.B) return;
   S.flag_out[b] = S.flag_step[b] = S.flag_acc[b] = 0;
-  S.m_full_step[b] = S.m_full_acc[b] = S.m_out_int[b] = 0;
+  S.m_full_step[b] = S.m_full_acc[b] = S.m_out_int[b] = S.m_loc_step[b] = 0;
   if (S.done[b]) return;
   const Cosmo &c = S.cosmo[b];
   const double target = S.etaout[(long long)b * MAX_OUT + S.i_out[b]];
@@ -214,6 +378,7 @@ __global__ void k_ctrl_begin(Batch S) {
     S.final_step[b] = fin;
     S.flag_step[b] = 1;
     S.m_full_step[b] = (c.sw_nl && !c.sw_1l);
+    S.m_loc_step[b] = !S.m_full_step[b];
     if (S.m_full_step[b]) S.counters[4LL * b + 3] += 5;  // integral evaluations of stages 2..6
     S.rmax_bits[b] = (unsigned long long)__double_as_longlong(DBL_MIN);
   } else {
@@ -397,6 +562,15 @@ void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *d
                 const int *mask, cudaStream_t st) {
   const int nrows = S.k_hi - S.k_lo;
   k_rhs<<<dim3((nrows + 127) / 128, S.B), 128, 0, st>>>(S, kgrid, yv, dyv, stage, mask);
+}
+static size_t attempt_smem_bytes() { return (size_t)RK_STAGES * (N_UP + N_UI + 24) * ATT_ROWS * sizeof(double); }
+int ode_configure() {
+  return (int)cudaFuncSetAttribute(k_attempt_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)attempt_smem_bytes());
+}
+void launch_attempt_local(const Batch &S, const double *kgrid, const int *mask, cudaStream_t st) {
+  const int nrows = S.k_hi - S.k_lo;
+  k_attempt_local<<<dim3((nrows + ATT_ROWS - 1) / ATT_ROWS, S.B), 128, attempt_smem_bytes(), st>>>(S, kgrid, mask);
 }
 void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st) {
   const long long n = (long long)N_U * S.nk;

@@ -95,6 +95,7 @@ struct Batch {
   unsigned long long *rmax_bits;
   int *i_out, *flag_out, *flag_step, *flag_acc, *final_step, *done;
   int *m_full_step, *m_full_acc, *m_out_int;  // masks of the integral launches
+  int *m_loc_step;  // stepping cosmologies whose RHS needs no new integrals (k_attempt_local)
   long long *counters;     // [B][4]
   long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
   int *act, *nact;         // [B], [1] compacted list of the cosmologies of the current launch
@@ -111,7 +112,7 @@ struct Batch {
 // numbers).  Off by default: a null Profiler* costs nothing.
 enum ProfCat {
   PC_EXTRAP, PC_BILINEAR, PC_JLO, PC_PZ, PC_ASSEMBLE, PC_RHS, PC_COMBINE, PC_FINAL, PC_CTRL,
-  PC_ACCEPT, PC_OUTPUT, PC_PREP_INPUTS, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
+  PC_ACCEPT, PC_OUTPUT, PC_ATTEMPT, PC_PREP_INPUTS, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
   PC_NCAT
 };
 #ifdef __CUDACC__
