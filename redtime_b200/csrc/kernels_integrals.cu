@@ -251,10 +251,15 @@ __global__ void __launch_bounds__(TPB, 2)
         w[2 * i] = v.x;
         w[2 * i + 1] = v.y;
       }
+      // window-major order: consecutive DFMAs share w[j]; per accumulator the lags still arrive
+      // in ascending order (bit-identical sums)
 #pragma unroll
-      for (int s = 0; s < VC; s++)
+      for (int j = 0; j < VC + R - 1; j++)
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r][q] = fma(tcur[s], w[s - r + R - 1], acc[r][q]);
+        for (int s = 0; s < VC; s++) {
+          const int r = s + R - 1 - j;
+          if (r >= 0 && r < R) acc[r][q] = fma(tcur[s], w[j], acc[r][q]);
+        }
     }
 #pragma unroll
     for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];

@@ -38,7 +38,7 @@ __device__ __forceinline__ bool ode_row_D_dD(const Batch &S, int b, int i, doubl
 // block belong to one cosmology and are evaluated at the same eta.  The rows then read their 41
 // state values, 38 sources and a few table entries: HBM traffic 960 B per row.
 struct RhsShared {
-  double eta, A, om10_den, Om11, z, a, pre4;
+  double eta, eeta, A, om10_den, Om11, z, a, pre4;
   RowX xb, xg;
   int beta_zero, beta_bad, growth_ok;
 };
@@ -46,6 +46,7 @@ struct RhsShared {
 __device__ __forceinline__ void rhs_time_setup(const Batch &S, const Cosmo &c, double eta, RhsShared &sh) {
   const double A = c.a_in * exp(eta);  // rt:1430
   sh.eta = eta;
+  sh.eeta = exp(eta);
   sh.A = A;
   sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
   sh.Om11 = 3.0 + bg_dlnH(c, A);
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(128)
   __syncthreads();
   const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.k_hi) return;
-  const double eta = sh.eta, eeta = exp(eta);
+  const double eeta = sh.eeta;
   const double k = kgrid[i];
   const int one_loop = c.sw_nl && c.sw_1l;
   const int evolve_Q = (S.print_Q || c.sw_pr);
@@ -158,17 +159,29 @@ __global__ void __launch_bounds__(128)
 // full Time-RG cosmologies (their stages are separated by integral evaluations).  HBM traffic:
 // y and the sources in, ynew out = 960 B per row instead of ~17.6 KB through the kernel chain.
 enum { ATT_ROWS = 32 };
-template <int NC>
-__device__ __forceinline__ void att_combine(const double *s_k, int stage, int lane, double h, const double *y,
-                                            double *yt) {
+template <int NC, int STAGE>
+__device__ __forceinline__ void att_combine_s(const double *s_k, int lane, double h, const double *y, double *yt) {
 #pragma unroll
   for (int j = 0; j < NC; j++) {
     double acc = 0.0;
-    for (int m = 0; m < stage; m++) {
-      const double a = RKF45::a(stage, m);
+#pragma unroll
+    for (int m = 0; m < STAGE; m++) {
+      const double a = RKF45::a(STAGE, m);
       if (a != 0.0) acc += a * s_k[(m * NC + j) * ATT_ROWS + lane];
     }
     yt[j] = y[j] + h * acc;
+  }
+}
+// ytmp of stage `stage` (the tableau row folds to constants in each case)
+template <int NC>
+__device__ __forceinline__ void att_combine(const double *s_k, int stage, int lane, double h, const double *y,
+                                            double *yt) {
+  switch (stage) {
+    case 1: att_combine_s<NC, 1>(s_k, lane, h, y, yt); break;
+    case 2: att_combine_s<NC, 2>(s_k, lane, h, y, yt); break;
+    case 3: att_combine_s<NC, 3>(s_k, lane, h, y, yt); break;
+    case 4: att_combine_s<NC, 4>(s_k, lane, h, y, yt); break;
+    default: att_combine_s<NC, 5>(s_k, lane, h, y, yt); break;
   }
 }
 template <int NC>
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int j = 0; j < N_UI; j++)
           A14[j] = !c.sw_nl ? 0.0 : one_loop ? pre * fp[a14_fpow(j)] * A0[j] : A0[j];
-        trg_rhs_PI(exp(sh[st].eta), k, s_om10[st][lane], sh[st].Om11, c.sw_nl, yt, A14, dy);
+        trg_rhs_PI(sh[st].eeta, k, s_om10[st][lane], sh[st].Om11, c.sw_nl, yt, A14, dy);
 #pragma unroll
         for (int j = 0; j < NC; j++) s_k[(st * NC + j) * ATT_ROWS + lane] = dy[j];
       }
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(128)
           }
 #pragma unroll
           for (int j = 0; j < NC; j++) R[j] = one_loop ? pre * fp[r24_fpow(8 * l + j)] * R0[j] : R0[j];
-          trg_rhs_Q(exp(sh[st].eta), s_om10[st][lane], sh[st].Om11, yt, R, dQ);
+          trg_rhs_Q(sh[st].eeta, s_om10[st][lane], sh[st].Om11, yt, R, dQ);
         } else {
 #pragma unroll
           for (int j = 0; j < NC; j++) dQ[j] = 0.0;
