@@ -479,7 +479,12 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   tb.n_terms = (int)terms.size();
   // which (kernel, beta-side spectrum) products each output group consumes
   std::memset(tb.need_cd, 0, sizeof tb.need_cd);
+  std::memset(tb.need_pz, 0, sizeof tb.need_pz);
   for (const AsmTerm &t : terms) {
+    if (t.src == 1) {  // PZ: index = 9 n + 3 ab + cd, the convolution itself is PZ_n(P_ab)
+      const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
+      tb.need_pz[gi] |= 1u << (3 * (t.index / 9) + (t.index % 9) / 3);
+    }
     if (t.src != 0 && t.src != 2) continue;  // J (kernels 0-6) and Jn0 (7-13)
     const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
     const int n = t.index / 9 + (t.src == 2 ? 7 : 0), cd = t.index % 3;

@@ -333,9 +333,10 @@ __global__ void __launch_bounds__(256)
 // PZb[e][n][ab][i] = dlnk/(2 pi^2) k_i^3 P00(k_i) sum_m P_ab(q_m) G_n[i_pad - m]
 __global__ void __launch_bounds__(128)
     k_pz(IntegralTabs tb, double pre, const double *__restrict__ P3, double *__restrict__ PZb,
-         int row0, int nrows, const int *__restrict__ mask) {
+         int row0, int nrows, const int *__restrict__ mask, unsigned int need) {
   const int e = blockIdx.y;
   if (mask && !mask[e]) return;
+  if (!((need >> blockIdx.x) & 1u)) return;  // no requested output consumes PZ_n(P_ab)
   const int n = blockIdx.x / 3, ab = blockIdx.x - 3 * n;
   extern __shared__ double s_p[];  // [np]
   const double *Pab = P3 + ((long long)e * 3 + ab) * tb.np;
@@ -484,11 +485,16 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     RT_TOC(prof, st);
     launches++;
   }
-  {
+  // P13-type log-convolutions: only those the requested groups consume (P_T,jm needs none)
+  unsigned int need_pz = 0;
+  for (int gi = 0; gi < 4; gi++)
+    if (groups & (1 << gi)) need_pz |= tb.need_pz[gi];
+  if (groups & GRP_RAW) need_pz = (1u << (N_ZKERN * 3)) - 1u;
+  if (need_pz) {
     dim3 g(N_ZKERN * 3, B);
     const double pre = tb.dlnk / (2.0 * M_PI * M_PI);  // rt:719
     RT_TIC(prof, PC_PZ, st);
-    k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask);
+    k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask, need_pz);
     RT_TOC(prof, st);
     launches++;
   }

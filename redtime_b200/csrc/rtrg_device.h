@@ -59,6 +59,7 @@ struct IntegralTabs {
   const double *ex_dx;    // [np] lnk - lnk[nk-1] for the power-law extrapolation, else 0
   // beta-side spectra (bit c = P_{cd=c}) of kernel n consumed by output group g = A, R, PT, PMR
   unsigned char need_cd[4][N_JKERN];
+  unsigned int need_pz[4];  // bit 3 n + ab: the PZ_n(P_ab) log-convolutions an output group consumes
   // assembly table (sorted by output row)
   int n_terms;
   const int *t_start;     // [56]
