@@ -24,7 +24,9 @@ def fake_runner(dirs, **cfg):           # stands in for the GPU pass of one rank
     return {d: (7 if d.endswith("M003") else 0) for d in dirs}
 dirs = ["/runs/M%03d" % i for i in range(1, 8)]
 res = batch.run_batch(dirs, runner=fake_runner, dist=dist)
-print("RESULT " + json.dumps({"rank": rank, "seen": seen, "res": res}), flush=True)
+# one file per rank: two ranks writing to the shared stdout pipe can interleave inside a line
+with open(os.path.join(sys.argv[2], "result_%d.json" % rank), "w") as f:
+    json.dump({"rank": rank, "seen": seen, "res": res}, f)
 dist.destroy_process_group()
 '''
 
@@ -57,10 +59,9 @@ def test_manifest_reader(tmp_path):
 def test_batch_front_end_world_size_2_gloo(tmp_path):
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
-    p = torchrun(2, [str(w), ROOT], 29611)
+    p = torchrun(2, [str(w), ROOT, str(tmp_path)], 29611)
     assert p.returncode == 0, p.stderr[-2000:]
-    outs = [json.loads(l[len("RESULT "):]) for l in p.stdout.split("\n") if l.startswith("RESULT ")]
-    assert len(outs) == 2
+    outs = [json.load(open(tmp_path / ("result_%d.json" % r))) for r in range(2)]
     by_rank = {o["rank"]: o for o in outs}
     assert by_rank[0]["seen"] == ["/runs/M001", "/runs/M003", "/runs/M005", "/runs/M007"]
     assert by_rank[1]["seen"] == ["/runs/M002", "/runs/M004", "/runs/M006"]
