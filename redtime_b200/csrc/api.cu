@@ -924,6 +924,7 @@ int rtrg_prepare(rtrg_handle *h) {
     S.m_full_acc = A.take<int>(B);
     S.m_out_int = A.take<int>(B);
     S.m_loc_step = A.take<int>(B);
+    S.att_time = A.take<double>((size_t)B * RK_STAGES * 48);  // RhsShared is < 48 doubles
     S.counters = A.take<long long>((size_t)4 * B);
     S.matvecs = A.take<long long>(B);
     S.act = A.take<int>(B);
@@ -1085,7 +1086,10 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, grp_out(h), 0, st, h->prof);
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
     // cosmologies without integrals inside the RHS (1-loop, linear): the whole attempt in one kernel
-    if (h->any_local) ODE_LAUNCH(PC_ATTEMPT, launch_attempt_local(S, h->d_kgrid, S.m_loc_step, st));
+    if (h->any_local) {
+      ODE_LAUNCH(PC_ATTEMPT, launch_attempt_local(S, h->d_kgrid, S.m_loc_step, st));
+      h->launches++;  // k_attempt_setup + k_attempt_local
+    }
     // full Time-RG: the stages are separated by integral evaluations (and the k-shard exchange)
     if (h->any_full) {
       for (int s = 1; s < RK_STAGES; s++) {

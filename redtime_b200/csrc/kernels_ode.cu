@@ -206,6 +206,16 @@ __device__ __forceinline__ double att_final(const Batch &S, const double *s_k, i
   }
   return r;
 }
+static_assert(sizeof(RhsShared) <= 48 * sizeof(double), "Batch::att_time slots are 48 doubles");
+// time-only quantities of the six stages, once per cosmology instead of once per 32-row block
+__global__ void k_attempt_setup(Batch S, const int *__restrict__ mask) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = idx / RK_STAGES, st = idx - b * RK_STAGES;
+  if (b >= S.B || !mask[b]) return;
+  RhsShared sh;
+  rhs_time_setup(S, S.cosmo[b], st == 0 ? S.t[b] : S.t[b] + RKF45::c(st) * S.h_try[b], sh);
+  reinterpret_cast<RhsShared *>(reinterpret_cast<double *>(S.att_time) + ((size_t)b * RK_STAGES + st) * 48)[0] = sh;
+}
 __global__ void __launch_bounds__(128)
     k_attempt_local(Batch S, const double *__restrict__ kgrid, const int *__restrict__ mask) {
   const int b = blockIdx.y;
@@ -217,8 +227,13 @@ __global__ void __launch_bounds__(128)
   __shared__ double s_r[4];
   extern __shared__ double s_kall[];  // PI: [6][17][32]; Q_l: [6][8][32] each
   const double h = S.h_try[b];
-  if (threadIdx.x < RK_STAGES)
-    rhs_time_setup(S, c, threadIdx.x == 0 ? S.t[b] : S.t[b] + RKF45::c(threadIdx.x) * h, sh[threadIdx.x]);
+  {  // stage quantities prepared by k_attempt_setup
+    const double *src = reinterpret_cast<const double *>(S.att_time) + (size_t)b * RK_STAGES * 48;
+    constexpr int ND = sizeof(RhsShared) / sizeof(double);
+    static_assert(sizeof(RhsShared) % sizeof(double) == 0, "copied as doubles");
+    for (int w = threadIdx.x; w < RK_STAGES * ND; w += blockDim.x)
+      reinterpret_cast<double *>(&sh[w / ND])[w % ND] = src[(w / ND) * 48 + w % ND];
+  }
   __syncthreads();
   const int i0 = S.k_lo + blockIdx.x * ATT_ROWS;
   for (int it = threadIdx.x; it < RK_STAGES * ATT_ROWS; it += blockDim.x) {
@@ -583,6 +598,7 @@ int ode_configure() {
 }
 void launch_attempt_local(const Batch &S, const double *kgrid, const int *mask, cudaStream_t st) {
   const int nrows = S.k_hi - S.k_lo;
+  k_attempt_setup<<<(S.B * RK_STAGES + 127) / 128, 128, 0, st>>>(S, mask);
   k_attempt_local<<<dim3((nrows + ATT_ROWS - 1) / ATT_ROWS, S.B), 128, attempt_smem_bytes(), st>>>(S, kgrid, mask);
 }
 void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st) {

@@ -97,6 +97,7 @@ struct Batch {
   int *i_out, *flag_out, *flag_step, *flag_acc, *final_step, *done;
   int *m_full_step, *m_full_acc, *m_out_int;  // masks of the integral launches
   int *m_loc_step;  // stepping cosmologies whose RHS needs no new integrals (k_attempt_local)
+  void *att_time;   // [B][RK_STAGES] time-only stage quantities of the current attempt (k_attempt_setup)
   long long *counters;     // [B][4]
   long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
   int *act, *nact;         // [B], [1] compacted list of the cosmologies of the current launch
