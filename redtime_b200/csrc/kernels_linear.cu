@@ -10,6 +10,8 @@
 //                   bookkeeping in shared memory (hdr:846-879, 932-963)
 //   k_init_state    initial conditions and the z1l linear spectrum (rt:1570-1586, 1299-1306)
 //   k_hook_*        stage-level parity hooks (D_dD, Beta_P, Plin*)
+#include <utility>
+
 #include "gk61_table.h"
 #include "rtrg_device.h"
 
@@ -171,6 +173,54 @@ struct GrowthRhsDev {
   }
 };
 
+// Prince-Dormand tableau as compile-time constants: the stage sums of growth_integrate_coop are
+// unrolled per stage with the zero entries removed (the generic loop spends two thirds of its
+// issue slots on tableau look-ups, tests and branches).  Same terms in the same order.
+struct PDc {
+  static constexpr double A[13][12] = {RT_PD_ROWS};
+  static constexpr double B8[13] = {RT_PD_B8};
+  static constexpr double B7[13] = {RT_PD_B7};
+};
+template <int S, int J>
+__device__ __forceinline__ void pd_term(const double (*k)[2], double &a0, double &a1) {
+  constexpr double a = PDc::A[S][J];
+  if (a != 0.0) {
+    a0 += a * k[J][0];
+    a1 += a * k[J][1];
+  }
+}
+template <int S, int... J>
+__device__ __forceinline__ void pd_acc_impl(const double (*k)[2], double &a0, double &a1,
+                                            std::integer_sequence<int, J...>) {
+  (pd_term<S, J>(k, a0, a1), ...);
+}
+__device__ __forceinline__ void pd_acc(int s, const double (*k)[2], double &a0, double &a1) {
+  switch (s) {
+#define RT_PD_CASE(S) case S: pd_acc_impl<S>(k, a0, a1, std::make_integer_sequence<int, S>()); break;
+    RT_PD_CASE(1) RT_PD_CASE(2) RT_PD_CASE(3) RT_PD_CASE(4) RT_PD_CASE(5) RT_PD_CASE(6)
+    RT_PD_CASE(7) RT_PD_CASE(8) RT_PD_CASE(9) RT_PD_CASE(10) RT_PD_CASE(11)
+    default: pd_acc_impl<12>(k, a0, a1, std::make_integer_sequence<int, 12>()); break;
+#undef RT_PD_CASE
+  }
+}
+template <int J>
+__device__ __forceinline__ void pd_bterm(const double (*k)[2], double (&s8)[2], double (&s7)[2]) {
+  constexpr double b8 = PDc::B8[J], b7 = PDc::B7[J];
+  if (b8 != 0.0) {
+    s8[0] += b8 * k[J][0];
+    s8[1] += b8 * k[J][1];
+  }
+  if (b7 != 0.0) {
+    s7[0] += b7 * k[J][0];
+    s7[1] += b7 * k[J][1];
+  }
+}
+template <int... J>
+__device__ __forceinline__ void pd_bsum(const double (*k)[2], double (&s8)[2], double (&s7)[2],
+                                        std::integer_sequence<int, J...>) {
+  (pd_bterm<J>(k, s8, s7), ...);
+}
+
 // Warp-cooperative form of growth_integrate (rtrg_math.h; same arithmetic per lane, bit for bit).
 // The lanes of a warp integrate the wavenumbers of ONE cosmology, and almost always in lock
 // step: every leg restarts from h = 1e-6 a (hdr:170-190), grows by the capped factor 5 and ends
@@ -183,8 +233,7 @@ __device__ void growth_integrate_coop(const GrowthRhsDev &g, double a_begin, dou
                                       bool valid, double *s_cf) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const double(*A)[12] = c_pd.A;
-  const double *C = c_pd.C, *B8 = c_pd.B8, *B7 = c_pd.B7;
+  const double *C = c_pd.C;
   double t = a_begin;
   const double t1 = a_end;
   double h = 1e-6 * t;
@@ -225,13 +274,7 @@ __device__ void growth_integrate_coop(const GrowthRhsDev &g, double a_begin, dou
       }
       for (int s = 1; s < 13; s++) {
         double acc0 = 0, acc1 = 0;
-        for (int j = 0; j < s; j++) {
-          const double a_sj = A[s][j];
-          if (a_sj != 0.0) {
-            acc0 += a_sj * k[j][0];
-            acc1 += a_sj * k[j][1];
-          }
-        }
+        pd_acc(s, k, acc0, acc1);
         const double yt[2] = {y0[0] + h0 * acc0, y0[1] + h0 * acc1};
         const double as = t0 + C[s] * h0;
         GrowthRhsDev::Coef c;
@@ -240,16 +283,7 @@ __device__ void growth_integrate_coop(const GrowthRhsDev &g, double a_begin, dou
         g.apply(as, c, yt, k[s]);
       }
       double s8[2] = {0, 0}, s7[2] = {0, 0};
-      for (int j = 0; j < 13; j++) {
-        if (B8[j] != 0.0) {
-          s8[0] += B8[j] * k[j][0];
-          s8[1] += B8[j] * k[j][1];
-        }
-        if (B7[j] != 0.0) {
-          s7[0] += B7[j] * k[j][0];
-          s7[1] += B7[j] * k[j][1];
-        }
-      }
+      pd_bsum(k, s8, s7, std::make_integer_sequence<int, 13>());
       const double yn[2] = {y0[0] + h0 * s8[0], y0[1] + h0 * s8[1]};
       const double ye[2] = {h0 * (s7[0] - s8[0]), h0 * (s7[1] - s8[1])};
       attempts++;
@@ -280,7 +314,7 @@ __device__ void growth_integrate_coop(const GrowthRhsDev &g, double a_begin, dou
   }
 }
 
-__global__ void __launch_bounds__(64) k_growth_ode(Batch S) {
+__global__ void __launch_bounds__(64, 7) k_growth_ode(Batch S) {  // 7 x 148 >= 1024 cosmologies: one wave
   const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   const Cosmo &c = S.cosmo[b];
   extern __shared__ double s_g[];  // [n_z] a nodes, [n_z][4] reciprocal denominators
