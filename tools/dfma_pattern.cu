@@ -27,6 +27,18 @@ __global__ void __launch_bounds__(352, WMODE == 1 ? 1 : 2) k_pat(const double *_
     for (int q = 0; q < 3; q++) acc[r][q] = 0.0;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    double wn[3][16];
+    if (WMODE == 4) {  // loop-carried: the windows used now were loaded during the previous chunk
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const double2 *wp = reinterpret_cast<const double2 *>(&s_w[q][((it + 1) & 31) * 8]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const double2 v = wp[i];
+          wn[q][2 * i] = v.x, wn[q][2 * i + 1] = v.y;
+        }
+      }
+    }
     if (WMODE == 3) {  // all three slots' windows at the top of the chunk: 96 registers' worth
 #pragma unroll
       for (int q = 0; q < 3; q++) {
@@ -75,6 +87,12 @@ __global__ void __launch_bounds__(352, WMODE == 1 ? 1 : 2) k_pat(const double *_
             acc[r][q] = fma(t[s], w[q][s - r + 7], acc[r][q]);
           }
       }
+    }
+    if (WMODE == 4) {
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) w[q][j] = wn[q][j];
     }
     // rotate t so that the compiler cannot hoist products out of the loop
     const double t0 = t[0];
@@ -147,6 +165,8 @@ int main() {
   RUN(2, 1, "row-major, windows in vector registers");
   RUN(0, 2, "lag-major, windows from LDS.128 per chunk");
   RUN(1, 2, "window-major, windows from LDS.128 per chunk");
+  RUN(0, 4, "lag-major, windows prefetched one chunk ahead (loop-carried)");
+  RUN(1, 4, "window-major, windows prefetched one chunk ahead");
   RUN(0, 3, "lag-major, all windows loaded at chunk top");
   RUN(1, 3, "window-major, all windows loaded at chunk top");
   return 0;
