@@ -29,7 +29,8 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
                      cudaStream_t st, Profiler *prof);
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st);
-int integrals_configure();
+int integrals_configure(const IntegralTabs &tb);
+size_t bilinear_smem_bytes(const IntegralTabs &tb);
 // kernels_linear.cu
 int linear_upload_constants();
 int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof);
@@ -50,7 +51,10 @@ void launch_final(const Batch &S, const int *mask, cudaStream_t st);
 void launch_ctrl_begin(const Batch &S, cudaStream_t st);
 void launch_ctrl_end(const Batch &S, int max_attempts, cudaStream_t st);
 void launch_accept(const Batch &S, cudaStream_t st);
-void launch_output(const Batch &S, const double *kgrid, cudaStream_t st);
+void launch_stash(const Batch &S, cudaStream_t st);
+void launch_vprep(const Batch &S, cudaStream_t st);
+void launch_output(const Batch &S, const double *kgrid, int v0, int nv, cudaStream_t st);
+void launch_loop_cond(unsigned long long handle, const Batch &S, long long max_rounds, cudaStream_t st);
 }  // namespace rtrg
 
 using namespace rtrg;
@@ -151,6 +155,7 @@ struct rtrg_handle {
   std::vector<long long> out_off, counters, matvecs;
   std::vector<int> ncols;
   size_t out_total = 0;
+  int vch = 0;  // virtual cosmologies (cosmology, output) per launch of the deferred output stage
   bool any_full = false, any_1loop = false, any_pr = false, any_local = false;
   double *d_yinit = nullptr, *d_raw = nullptr, *d_scratch = nullptr;
   int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
@@ -364,8 +369,6 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     rtrg_destroy(h);
     return fail(RTRG_ECUDA, "constant upload failed");
   }
-  integrals_configure();
-  ode_configure();
 
   const GridSpec &g = h->grid;
   const int nk = g.nk, np = g.np;
@@ -381,9 +384,26 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   tb.LP = tb.NVp + BIL_R;
   tb.NUp = nk - BIL_R + tb.NVp;
   tb.ldT = (nk + g.nsup - 1 + 7) / 8 * 8;
-  tb.nchunk = (tb.NV + 352 - 1) / 352;
+  tb.tpb = BIL_TPB;
+  tb.nchunk = (tb.NV + BIL_TPB - 2) / BIL_TPB + 1;
   tb.vsplit = cfg->v_split;
   tb.dlnk = g.dlnk;
+  {
+    // the bilinear kernel stages 9 spectra of LP samples in shared memory, two CTAs per SM
+    int smem_optin = 0;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const size_t need = bilinear_smem_bytes(tb) + 1024;
+    if (need > (size_t)smem_optin) {
+      rtrg_destroy(h);
+      return fail(RTRG_EINVAL, "nk = %d needs %zu bytes of shared memory per CTA, the device offers %d (nk <= 512 fits)",
+                  cfg->nk, need, smem_optin);
+    }
+    if (integrals_configure(tb) != 0 || ode_configure() != 0) {
+      cudaGetLastError();
+      rtrg_destroy(h);
+      return fail(RTRG_ECUDA, "cudaFuncSetAttribute(shared memory opt-in) failed");
+    }
+  }
 
   // --- circulant kernels, built in parallel on the host, packed into the compact layout
   const int UMIN = g.nshift - (np - 1), NU = nk + g.nsup - 1;
@@ -863,6 +883,15 @@ int rtrg_prepare(rtrg_handle *h) {
   }
   h->out_total = off;
   S.n_zmax = n_zmax;
+  // virtual cosmologies of the deferred output stage: one per (cosmology, output redshift)
+  std::vector<int> vbase(B), vc_b, vc_io;
+  for (int b = 0; b < B; b++) {
+    vbase[b] = (int)vc_b.size();
+    for (int io = 0; io < h->cos[b].c.n_out; io++) vc_b.push_back(b), vc_io.push_back(io);
+  }
+  S.NO = (int)vc_b.size();
+  h->vch = std::min(S.NO, 8192);
+  const size_t BV = (size_t)std::max(B, h->vch);  // integral work space: per cosmology or per virtual one
   // growth-table axes (hdr:677-687)
   std::vector<double> lna(cfg.n_lna + 1), lnkg(cfg.n_lnk + 1);
   {
@@ -905,11 +934,11 @@ int rtrg_prepare(rtrg_handle *h) {
     S.kst = A.take<double>(RK_STAGES * NE);
     h->d_yinit = A.take<double>(NE);
     S.src = A.take<double>((size_t)B * N_SRC * nk);
-    S.Prev = A.take<double>((size_t)B * 3 * tb.LP);
-    S.P3 = A.take<double>((size_t)B * 3 * np);
-    S.Jpart = A.take<double>((size_t)B * N_JKERN * tb.nchunk * tb.vsplit * 9 * nk);
-    S.PZb = A.take<double>((size_t)B * N_ZKERN * 3 * nk);
-    S.Jlo = A.take<double>(B);
+    S.Prev = A.take<double>(BV * 3 * tb.LP);
+    S.P3 = A.take<double>(BV * 3 * np);
+    S.Jpart = A.take<double>(BV * N_JKERN * tb.nchunk * tb.vsplit * 9 * nk);
+    S.PZb = A.take<double>(BV * N_ZKERN * 3 * nk);
+    S.Jlo = A.take<double>(BV);
     S.t = A.take<double>(B);
     S.h = A.take<double>(B);
     S.h_try = A.take<double>(B);
@@ -927,9 +956,20 @@ int rtrg_prepare(rtrg_handle *h) {
     S.att_time = A.take<double>((size_t)B * RK_STAGES * 48);  // RhsShared is < 48 doubles
     S.counters = A.take<long long>((size_t)4 * B);
     S.matvecs = A.take<long long>(B);
-    S.act = A.take<int>(B);
+    S.act = A.take<int>(BV);
     S.nact = A.take<int>(1);
     S.n_active = A.take<int>(1);
+    S.rounds = A.take<long long>(1);
+    S.ystash = A.take<double>((size_t)S.NO * N_U * nk);
+    S.t_stash = A.take<double>(S.NO);
+    S.vbase = A.take<int>(B);
+    S.vc_b = A.take<int>(S.NO);
+    S.vc_io = A.take<int>(S.NO);
+    S.vc_have = A.take<int>(S.NO);
+    S.vc_mask = A.take<int>(S.NO);
+    S.cosmo_v = A.take<Cosmo>(S.NO);
+    S.matvecs_v = A.take<long long>(S.NO);
+    S.src_v = A.take<double>((size_t)h->vch * N_SRC * nk);
     S.out = A.take<double>(h->out_total);
     S.hdr = A.take<double>((size_t)B * MAX_OUT * 5);
     S.hdr0 = A.take<double>((size_t)B * 2);
@@ -981,6 +1021,9 @@ int rtrg_prepare(rtrg_handle *h) {
   CU(cudaMemcpyAsync(d_lnkg, lnkg.data(), lnkg.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.out_off, h->out_off.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.ncols, h->ncols.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.vbase, vbase.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.vc_b, vc_b.data(), vc_b.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(S.vc_io, vc_io.data(), vc_io.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   h->launches += launch_prep_inputs(S, h->d_T0, max_rows, st, h->prof);
   CU(cudaStreamSynchronize(st));  // the host vectors above go out of scope
   h->uploaded = true;
@@ -998,6 +1041,7 @@ int rtrg_device_init(rtrg_handle *h) {
   const size_t NE = (size_t)B * N_U * nk;
   cudaStream_t st = h->stream;
   CU(cudaMemsetAsync(S.matvecs, 0, B * sizeof(long long), st));
+  CU(cudaMemsetAsync(S.matvecs_v, 0, S.NO * sizeof(long long), st));
   h->launches += launch_linear_init(S, h->d_kgrid, st, h->prof);
   CU(cudaMemcpyAsync(h->d_yinit, S.y, NE * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (h->any_1loop) {
@@ -1046,6 +1090,8 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   CU(cudaMemcpyAsync(S.done, done0.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(S.counters, 0, 4 * B * sizeof(long long), st));
   CU(cudaMemcpyAsync(S.n_active, &n_active, sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(S.rounds, 0, sizeof(long long), st));
+  CU(cudaMemsetAsync(S.vc_have, 0, S.NO * sizeof(int), st));
 
   // --- k-sharded mode: all-gather of the ranks' ln P rows, max-reduction of the error norm
   const bool sharded = h->cfg.k_shards > 1;
@@ -1076,15 +1122,17 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
 
   long long rounds = 0;
   const long long max_rounds = (long long)h->cfg.max_attempts + RTRG_MAX_OUT + 8;
-  // One round = every unfinished cosmology attempts one RKF45 step or emits one table.  The
-  // launch sequence of a round is the same every time (what differs lives in device-side masks),
-  // so it is captured once into a CUDA graph and replayed: a round is ~25-60 launches (+ the NCCL
-  // exchanges when k-sharded), which is launch-latency bound for small batches.
+  // One round = every unfinished cosmology attempts one RKF45 step or reaches one output
+  // redshift (its state is stashed; the tables are produced after the loop).  The launch
+  // sequence of a round is the same every time -- what differs lives in device-side masks -- so
+  // it is captured once.  Unsharded runs put it into the body of a conditional WHILE graph node
+  // whose condition (cosmologies still active) is set by the last kernel of the body: the whole
+  // evolution is ONE graph launch and one host synchronisation.  k-sharded runs over NCCL replay a
+  // per-round graph (NCCL's capture may add host nodes, which a conditional body cannot hold) and
+  // read one int back per round.
   auto round_body = [&]() -> int {
     ODE_LAUNCH(PC_CTRL, launch_ctrl_begin(S, st));
-    if (h->any_1loop && grp_out(h))
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_out_int, grp_out(h), 0, st, h->prof);
-    ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, st));
+    ODE_LAUNCH(PC_OUTPUT, launch_stash(S, st));
     // cosmologies without integrals inside the RHS (1-loop, linear): the whole attempt in one kernel
     if (h->any_local) {
       ODE_LAUNCH(PC_ATTEMPT, launch_attempt_local(S, h->d_kgrid, S.m_loc_step, st));
@@ -1113,49 +1161,120 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   // no graph while per-kernel timing is on (events between the nodes), for the host-driven
   // loopback exchange, or when RTRG_NO_GRAPH is set
   const bool use_graph = !h->prof && (!sharded || h->xch->capturable()) && !std::getenv("RTRG_NO_GRAPH");
+  const bool use_while = use_graph && (!sharded || h->xch->device_side()) && !std::getenv("RTRG_NO_WHILE");
   cudaGraphExec_t gexec = nullptr;
   long long launches_per_round = 0;
-  if (use_graph && n_active > 0 &&
-      cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();  // e.g. the legacy default stream cannot be captured: plain launches then
-  } else if (use_graph && n_active > 0) {
-    cudaGraph_t graph = nullptr;
-    const long long l0 = h->launches;
-    const int rc_body = round_body();
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    launches_per_round = h->launches - l0;
-    h->launches = l0;
-    if (rc_body != RTRG_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc_body;
+  bool whole_loop_graph = false;
+  if (use_while && n_active > 0) {
+    // graph = { WHILE(cond) { round ; cond = n_active > 0 && rounds < max } }
+    cudaGraph_t graph = nullptr, body = nullptr;
+    cudaGraphConditionalHandle cond = 0;
+    cudaGraphNode_t node = nullptr;
+    cudaGraphNodeParams np_ = {};
+    cudaError_t ce = cudaGraphCreate(&graph, 0);
+    if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault);
+    if (ce == cudaSuccess) {
+      np_.type = cudaGraphNodeTypeConditional;
+      np_.conditional.handle = cond;
+      np_.conditional.type = cudaGraphCondTypeWhile;
+      np_.conditional.size = 1;
+      ce = cudaGraphAddNode(&node, graph, nullptr, 0, &np_);
     }
-    if (ce != cudaSuccess) return fail(RTRG_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) return fail(RTRG_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
-  }
-  while (n_active > 0 && rounds < max_rounds) {
-    if (gexec) {
-      const cudaError_t ge = cudaGraphLaunch(gexec, st);
-      if (ge != cudaSuccess) {
-        cudaGraphExecDestroy(gexec);
-        return fail(RTRG_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(ge));
-      }
-      h->launches += launches_per_round;
-    } else {
+    if (ce == cudaSuccess) {
+      body = np_.conditional.phGraph_out[0];
+      ce = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    }
+    if (ce == cudaSuccess) {
+      const long long l0 = h->launches;
       const int rc_body = round_body();
-      if (rc_body != RTRG_OK) return rc_body;
+      launch_loop_cond((unsigned long long)cond, S, max_rounds, st);
+      cudaGraph_t captured = nullptr;
+      ce = cudaStreamEndCapture(st, &captured);
+      launches_per_round = h->launches - l0 + 1;
+      h->launches = l0;
+      if (rc_body != RTRG_OK) {
+        cudaGraphDestroy(graph);
+        return rc_body;
+      }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
     }
-    cudaError_t e1 = cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
-    if (e1 != cudaSuccess) {
-      if (gexec) cudaGraphExecDestroy(gexec);
-      return fail(RTRG_ECUDA, "round %lld: %s", rounds, cudaGetErrorString(e1));
+    if (graph) cudaGraphDestroy(graph);
+    if (ce == cudaSuccess) {
+      whole_loop_graph = true;
+    } else {
+      cudaGetLastError();  // conditional nodes unavailable (old driver): per-round graph below
+      gexec = nullptr;
     }
-    rounds++;
   }
-  if (gexec) cudaGraphExecDestroy(gexec);
+  if (whole_loop_graph) {
+    cudaError_t e1 = cudaGraphLaunch(gexec, st);
+    if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(&rounds, S.rounds, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(gexec);
+    gexec = nullptr;
+    if (e1 != cudaSuccess) return fail(RTRG_ECUDA, "evolution graph: %s", cudaGetErrorString(e1));
+    h->launches += launches_per_round * rounds;
+  } else {
+    if (use_graph && n_active > 0 &&
+        cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();  // e.g. the legacy default stream cannot be captured: plain launches then
+    } else if (use_graph && n_active > 0) {
+      cudaGraph_t graph = nullptr;
+      const long long l0 = h->launches;
+      const int rc_body = round_body();
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      launches_per_round = h->launches - l0;
+      h->launches = l0;
+      if (rc_body != RTRG_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc_body;
+      }
+      if (ce != cudaSuccess) return fail(RTRG_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+      const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return fail(RTRG_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+    }
+    while (n_active > 0 && rounds < max_rounds) {
+      if (gexec) {
+        const cudaError_t ge = cudaGraphLaunch(gexec, st);
+        if (ge != cudaSuccess) {
+          cudaGraphExecDestroy(gexec);
+          return fail(RTRG_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(ge));
+        }
+        h->launches += launches_per_round;
+      } else {
+        const int rc_body = round_body();
+        if (rc_body != RTRG_OK) return rc_body;
+      }
+      cudaError_t e1 = cudaMemcpyAsync(&n_active, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+      if (e1 != cudaSuccess) {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        return fail(RTRG_ECUDA, "round %lld: %s", rounds, cudaGetErrorString(e1));
+      }
+      rounds++;
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+  }
   CU(cudaGetLastError());
+
+  // --- deferred output stage: the 1-loop output integrals of every stashed (cosmology, output)
+  // state (rt:1646-1653) in launches of up to vch virtual cosmologies, then the tables
+  ODE_LAUNCH(PC_CTRL, launch_vprep(S, st));
+  const bool out_int = h->any_1loop && grp_out(h);
+  for (int v0 = 0; v0 < S.NO; v0 += h->vch) {
+    const int nv = std::min(h->vch, S.NO - v0);
+    if (out_int) {
+      Batch SV = S;
+      SV.B = nv;
+      SV.cosmo = S.cosmo_v + v0;
+      SV.matvecs = S.matvecs_v + v0;
+      h->launches += launch_integrals(tb, SV, S.ystash + (size_t)v0 * N_U * nk, (long long)N_U * nk, S.src_v, nullptr,
+                                      S.vc_mask + v0, grp_out(h), 0, st, h->prof);
+    }
+    ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, v0, nv, st));
+  }
   if (sharded) {  // every rank ends up with the complete tables
     std::vector<Segment> segs;
     for (int b = 0; b < B; b++)
@@ -1172,6 +1291,8 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   h->matvecs.assign(B, 0);
   CU(cudaMemcpyAsync(h->counters.data(), S.counters, 4 * B * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->matvecs.data(), S.matvecs, B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  std::vector<long long> mv_v(S.NO);
+  CU(cudaMemcpyAsync(mv_v.data(), S.matvecs_v, S.NO * sizeof(long long), cudaMemcpyDeviceToHost, st));
   std::vector<Cosmo> cs(B);
   CU(cudaMemcpyAsync(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1184,6 +1305,8 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     if (status) status[b] = cs[b].status;
     if (cs[b].status) worst = RTRG_EODE;
   }
+  for (int b = 0, v = 0; b < B; b++)  // sets executed by the deferred output stage
+    for (int io = 0; io < h->cos[b].c.n_out; io++, v++) h->matvecs[b] += mv_v[v];
   if (n_active > 0) return fail(RTRG_EODE, "integration did not finish within %lld rounds", max_rounds);
   if (worst) return fail(worst, "at least one cosmology failed (see status[])");
   return RTRG_OK;

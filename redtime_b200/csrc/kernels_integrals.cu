@@ -157,39 +157,51 @@ __global__ void k_compact(const int *__restrict__ mask, int B, int *__restrict__
   if (lane == 0) *nact = off;
 }
 
-// R: output rows per CTA; TPB: threads (one alpha-side lag each); VC: beta-side lags per
-// software-pipelined chunk.  Grid: (row blocks x lag chunks, items, ceil(B * 3 / 3)).
+// R: output rows per row block; TPB: threads; VC: beta-side lags per software-pipelined chunk.
+//
+// Work distribution.  A row block (R consecutive output rows) needs one thread per alpha-side lag,
+// NV = nsup + R - 1 of them (334 at nk = 128), each streaming its own column of the shifted T_n
+// window.  The (row block, lag) pairs of ALL row blocks are laid out on one axis, item = rb NV + tu,
+// and cut into CTAs of TPB = 384 consecutive items: 12 full warps per CTA, 24 per SM -- every lane
+// of every warp owns a lag (16 row blocks x 334 lags fill 13.92 CTAs, the 14th is 92 % full) and
+// the four schedulers of an SM hold six warps each.  (One CTA per row block left 18 of its 352
+// threads idle and spread 22 warps 6/6/6/4.)  A CTA therefore touches up to three row blocks; this
+// costs nothing inside the main loop because the beta-side windows do not depend on the row block
+// (T_n is shifted along its diagonal, the spectra are not), and the epilogue reduces the lags of
+// each row block separately.  The item axis is global (independent of k-sharding), so a sharded
+// run adds the same numbers in the same order as the unsharded one.
+// Grid: (CTAs along the item axis x v_split, items of the launch, slot triples).
 template <int R, int TPB, int VC>
 __global__ void __launch_bounds__(TPB, 2)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
-               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int row0,
+               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
                const int *__restrict__ act, const int *__restrict__ nact) {
-  constexpr int NS = 3;
+  constexpr int NS = 3, NWARP = TPB / 32;
   const BilItem item = L.it[blockIdx.y];
   const int n = item.n, ncd = item.ncd;
   const int nslots = (*nact) * ncd;
   const int slot0 = NS * blockIdx.z;
   if (slot0 >= nslots) return;
-  // blockIdx.x = (row block, split of the beta-side lags, chunk of the alpha-side lags)
-  const int nch = tb.nchunk * tb.vsplit;
-  const int rb = blockIdx.x / nch, part = blockIdx.x - rb * nch;
-  const int vs = part / tb.nchunk, chunk = part - vs * tb.nchunk;
+  // blockIdx.x = (CTA along the item axis, split of the beta-side lags)
+  const int cx = blockIdx.x / tb.vsplit, vs = blockIdx.x - cx * tb.vsplit;
+  const int c = c_lo + cx;
   extern __shared__ __align__(128) double sm[];
   double *s_a = sm;                     // [NS][3][LP]: the three spectra of each slot's cosmology
-  double *s_red = sm + NS * 3 * tb.LP;  // [TPB/32][9R]
+  double *s_red = sm + NS * 3 * tb.LP;  // [NWARP][2][9R]
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int s_wrb[NWARP][2];       // row block(s) the lanes of each warp belong to
+  __shared__ int s_e[NS], s_cd[NS], s_ok[NS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int LP = tb.LP, ldT = tb.ldT;
   const uint32_t bytes = 3u * (uint32_t)LP * 8u;
 
   int e_q[NS], cd_q[NS];
-  bool ok_q[NS];
 #pragma unroll
   for (int q = 0; q < NS; q++) {
     const int sl = min(slot0 + q, nslots - 1);
-    ok_q[q] = (slot0 + q) < nslots;
     e_q[q] = act[sl / ncd];
     cd_q[q] = item.cd[sl - (sl / ncd) * ncd];
+    if (tid == 0) s_e[q] = e_q[q], s_cd[q] = cd_q[q], s_ok[q] = (slot0 + q) < nslots;
   }
 
   if (tid == 0) mbar_init(&mbar, 1);
@@ -200,12 +212,14 @@ __global__ void __launch_bounds__(TPB, 2)
     for (int q = 0; q < NS; q++) tma_bulk_g2s(s_a + q * 3 * LP, Prev + (long long)e_q[q] * 3 * LP, bytes, &mbar);
   }
 
-  const int i0 = row0 + rb * R;
-  const int tu = chunk * TPB + tid;
-  const bool active = tu < tb.NV;
-  const int tuc = active ? tu : tb.NV - 1;
+  // this thread's (row block, alpha-side lag)
+  const int it0 = c * TPB + tid;
+  const int rb_true = it0 / tb.NV, tu = it0 - rb_true * tb.NV;
+  const bool active = rb_true >= rb_lo && rb_true < rb_hi;
+  const int rb = min(max(rb_true, rb_lo), rb_hi - 1);  // idle lanes stream a valid column, add zeros
+  const int i0 = rb * R;
   // T stream: 16-byte elements holding two consecutive beta-side lags (LDG.128, coalesced in u)
-  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tuc;
+  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tu;
   const double *s_c[NS];
 #pragma unroll
   for (int q = 0; q < NS; q++) s_c[q] = s_a + (q * 3 + cd_q[q]) * LP;
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(TPB, 2)
         w[2 * i + 1] = v.y;
       }
       // window-major order: consecutive DFMAs share w[j]; per accumulator the lags still arrive
-      // in ascending order (bit-identical sums)
+      // in ascending order
 #pragma unroll
       for (int j = 0; j < VC + R - 1; j++)
 #pragma unroll
@@ -265,37 +279,55 @@ __global__ void __launch_bounds__(TPB, 2)
     for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
   }
 
-  // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r] * S_u[r]; s_red slot = q*3 + ab
-  static_assert(R == 8, "the epilogue reduction is written for 8 rows per CTA");
+  // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r] * S_u[r], the sum running over the
+  // lags of ONE row block.  A warp holds lanes of one row block, or of two when it straddles a
+  // block boundary (about one warp in ten): side 0 = the block of lane 0, side 1 = that of lane 31.
+  static_assert(R == 8, "the epilogue reduction is written for 8 rows per row block");
+  const int rbA = __shfl_sync(0xffffffffu, rb_true, 0), rbB = __shfl_sync(0xffffffffu, rb_true, 31);
+  const int nside = (rbA == rbB) ? 1 : 2;
+  if (lane == 0) s_wrb[warp][0] = rbA, s_wrb[warp][1] = (nside == 2) ? rbB : -1;
   const int nab = L.replicate ? 1 : 3;
 #pragma unroll
   for (int q = 0; q < NS; q++) {
     for (int ab = 0; ab < nab; ab++) {
-      double prod[R];
+      for (int side = 0; side < nside; side++) {
+        const bool mine = active && rb_true == (side ? rbB : rbA);
+        double prod[R];
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const double m = active ? s_a[(q * 3 + ab) * LP + (R - 1) + tu - r] : 0.0;
-        prod[r] = m * acc[r][q];
+        for (int r = 0; r < R; r++) {
+          const double m = mine ? s_a[(q * 3 + ab) * LP + (R - 1) + tu - r] : 0.0;
+          prod[r] = m * acc[r][q];
+        }
+        warp_sum_multi<R>(prod, lane);
+        if ((lane & 3) == 0) s_red[(warp * 2 + side) * (9 * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
       }
-      warp_sum_multi<R>(prod, lane);
-      if ((lane & 3) == 0) s_red[warp * (9 * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
     }
   }
   __syncthreads();
-  if (tid < 9 * R) {
-    const int slot = tid / R, r = tid - slot * R, q = slot / 3, ab = slot - 3 * q;
+  // one thread per (row block of this CTA, slot, ab, row): add the warps' partial sums in warp
+  // order and store this CTA's part of the row block
+  const int rb_first = (c * TPB) / tb.NV, nrbl = (c * TPB + TPB - 1) / tb.NV - rb_first + 1;
+  const int nch = tb.nchunk * tb.vsplit;
+  for (int idx = tid; idx < nrbl * 9 * R; idx += TPB) {
+    const int rbl = idx / (9 * R), x = idx - rbl * (9 * R), rbx = rb_first + rbl;
+    if (rbx < rb_lo || rbx >= rb_hi) continue;
+    const int slot = x / R, r = x - slot * R, q = slot / 3, ab = slot - 3 * q;
+    const int e = s_e[q];
     // Jn0 only feeds the RSD terms (rt:804): cosmologies without them keep their old entries
-    if (ok_q[q] && ab < nab && !(n >= 7 && !cosmo[e_q[q]].sw_pr)) {
-      double s = 0.0;
+    if (!s_ok[q] || ab >= nab || (n >= 7 && !cosmo[e].sw_pr)) continue;
+    double s = 0.0;
 #pragma unroll 1
-      for (int wv = 0; wv < TPB / 32; wv++) s += s_red[wv * (9 * R) + tid];
-      double *dst = Jpart + (((long long)e_q[q] * N_JKERN + n) * nch + part) * 9 * tb.nk + i0 + r;
-      if (L.replicate) {
+    for (int wv = 0; wv < NWARP; wv++) {
+      if (s_wrb[wv][0] == rbx) s += s_red[(wv * 2) * (9 * R) + x];
+      if (s_wrb[wv][1] == rbx) s += s_red[(wv * 2 + 1) * (9 * R) + x];
+    }
+    const int part = vs * tb.nchunk + (c - (rbx * tb.NV) / TPB);
+    double *dst = Jpart + (((long long)e * N_JKERN + n) * nch + part) * 9 * tb.nk + rbx * R + r;
+    if (L.replicate) {
 #pragma unroll
-        for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
-      } else {
-        dst[(long long)(ab * 3 + cd_q[q]) * tb.nk] = s;
-      }
+      for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
+    } else {
+      dst[(long long)(ab * 3 + s_cd[q]) * tb.nk] = s;
     }
   }
 }
@@ -384,9 +416,13 @@ __global__ void __launch_bounds__(256)
       const int iJ = (v < 63) ? v : v - 126;
       const int n = iJ / 9 + ((v < 63) ? 0 : 7), pair = iJ % 9;
       if (v < 63 || has_jn0) {
-        const int nch = tb.nchunk * tb.vsplit;
-        for (int ch = 0; ch < nch; ch++)
-          x += Jpart[((((long long)e * N_JKERN + n) * nch + ch) * 9 + pair) * tb.nk + i];
+        // the parts k_bilinear wrote for this row block: per split of the beta-side lags, one per
+        // CTA along the item axis that holds some of the block's alpha-side lags
+        const int nch = tb.nchunk * tb.vsplit, rb = i / BIL_R;
+        const int np_rb = (rb * tb.NV + tb.NV - 1) / tb.tpb - (rb * tb.NV) / tb.tpb + 1;
+        for (int vs = 0; vs < tb.vsplit; vs++)
+          for (int p = 0; p < np_rb; p++)
+            x += Jpart[((((long long)e * N_JKERN + n) * nch + vs * tb.nchunk + p) * 9 + pair) * tb.nk + i];
         x *= tb.kfac[n * tb.nk + i];
       }
     } else if (v < 126) {
@@ -424,10 +460,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------- launchers
-enum { BIL_TPB = 352 };
-
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
-  return (size_t)(9 * tb.LP + (BIL_TPB / 32) * 9 * BIL_R) * sizeof(double);
+  return (size_t)(9 * tb.LP + (BIL_TPB / 32) * 2 * 9 * BIL_R) * sizeof(double);
 }
 
 // Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
@@ -473,9 +507,12 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     // slot count exit at once
     int maxncd = 1;
     for (int i = 0; i < nitems; i++) maxncd = std::max(maxncd, (int)L.it[i].ncd);
-    dim3 g((nrows / BIL_R) * tb.nchunk * tb.vsplit, nitems, (B * maxncd + 2) / 3);
-    k_bilinear<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, row0,
-                                                                             S.act, S.nact);
+    // CTAs along the global (row block, lag) axis that hold lags of this rank's row blocks
+    const int rb_lo = row0 / BIL_R, rb_hi = (row0 + nrows) / BIL_R;
+    const int c_lo = (rb_lo * tb.NV) / BIL_TPB, c_hi = (rb_hi * tb.NV - 1) / BIL_TPB;
+    dim3 g((c_hi - c_lo + 1) * tb.vsplit, nitems, (B * maxncd + 2) / 3);
+    k_bilinear<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo,
+                                                                             rb_hi, c_lo, S.act, S.nact);
     launches++;
   }
   RT_TOC(prof, st);
@@ -515,10 +552,10 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
   k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, nullptr, 0);
 }
 
-int integrals_configure() {
+int integrals_configure(const IntegralTabs &tb) {
   // opt in to the dynamic shared memory the bilinear kernel needs on large grids
   return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   110 * 1024);
+                                   (int)bilinear_smem_bytes(tb));
 }
 
 }  // namespace rtrg

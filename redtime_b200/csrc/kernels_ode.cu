@@ -475,13 +475,40 @@ __global__ void k_accept(Batch S) {
   S.y[(long long)b * n + idx] = S.ynew[(long long)b * n + idx];
 }
 
-// ---------------------------------------------------------------------------- k_output
-// columns of one row as in rt:1670-1737
-__global__ void __launch_bounds__(128) k_output(Batch S, const double *__restrict__ kgrid) {
+// ---------------------------------------------------------------------------- k_stash
+// Round loop, cosmologies that reached an output redshift: keep the state for the deferred
+// output stage (the evolution itself never consumes the output integrals, rt:1646-1653).
+__global__ void k_stash(Batch S) {
   const int b = blockIdx.y;
   if (!S.flag_out[b]) return;
+  const long long n = (long long)N_U * S.nk;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = S.vbase[b] + S.i_out[b];
+  if (idx == 0) {
+    S.vc_have[v] = 1;
+    S.t_stash[v] = S.t[b];
+  }
+  if (idx < n) S.ystash[(long long)v * n + idx] = S.y[(long long)b * n + idx];
+}
+// after the loop: which virtual cosmologies need the 1-loop output integrals (rt:1646), and the
+// per-virtual copy of the cosmology record the integral kernels index
+__global__ void k_vprep(Batch S) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= S.NO) return;
+  const Cosmo c = S.cosmo[S.vc_b[v]];
+  S.cosmo_v[v] = c;
+  S.vc_mask[v] = S.vc_have[v] && c.sw_nl && c.sw_1l;
+}
+
+// ---------------------------------------------------------------------------- k_output
+// columns of one row as in rt:1670-1737, for the virtual cosmologies [v0, v0 + gridDim.y);
+// src_v holds the output integrals of that chunk
+__global__ void __launch_bounds__(128) k_output(Batch S, const double *__restrict__ kgrid, int v0) {
+  const int v = v0 + blockIdx.y;
+  if (!S.vc_have[v]) return;
+  const int b = S.vc_b[v], io = S.vc_io[v];
   const Cosmo &c = S.cosmo[b];
-  const int nk = S.nk, io = S.i_out[b];
+  const int nk = S.nk;
   const double z = S.zout[(long long)b * MAX_OUT + io], a = S.aout[(long long)b * MAX_OUT + io];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
@@ -489,7 +516,7 @@ __global__ void __launch_bounds__(128) k_output(Batch S, const double *__restric
     const GrowthTab gt = growth_tab(S, b);
     double D = NAN, dD = NAN;
     growth_D_dD(gt, z, 1e-3, &D, &dD);  // hdr:964-965
-    h[0] = S.t[b];
+    h[0] = S.t_stash[v];
     h[1] = a;
     h[2] = z;
     h[3] = sqrt(bg_H2(c, a)) * H0H;
@@ -505,7 +532,7 @@ __global__ void __launch_bounds__(128) k_output(Batch S, const double *__restric
   const double k = kgrid[i];
   const int ncols = S.ncols[b];
   double *row = S.out + S.out_off[b] + ((long long)io * nk + i) * ncols;
-  const double *y = S.y + (long long)b * N_U * nk + i;
+  const double *y = S.ystash + (long long)v * N_U * nk + i;
   const double a_ain = a / c.a_in, a2 = a_ain * a_ain, a3 = a2 * a_ain, a4 = a2 * a2;
   int col = 0;
   row[col++] = k;
@@ -550,7 +577,7 @@ __global__ void __launch_bounds__(128) k_output(Batch S, const double *__restric
   row[col++] = exp(y[2LL * nk]) * a2;
   const bool have_int = (c.sw_nl && c.sw_1l);  // rt:1646; otherwise the reference prints
                                                // uninitialised memory (zeros in its goldens)
-  const double *s1 = S.src + (long long)b * N_SRC * nk + i;
+  const double *s1 = S.src_v + (long long)(v - v0) * N_SRC * nk + i;
   if (S.print_A)
     for (int j = 0; j < N_UI; j++) row[col++] = have_int ? s1[(long long)j * nk] : 0.0;
   if (S.print_I)
@@ -617,8 +644,22 @@ void launch_accept(const Batch &S, cudaStream_t st) {
   const long long n = (long long)N_U * S.nk;
   k_accept<<<dim3((unsigned)((n + 255) / 256), S.B), 256, 0, st>>>(S);
 }
-void launch_output(const Batch &S, const double *kgrid, cudaStream_t st) {
-  k_output<<<dim3((S.nk + 127) / 128, S.B), 128, 0, st>>>(S, kgrid);
+void launch_stash(const Batch &S, cudaStream_t st) {
+  const long long n = (long long)N_U * S.nk;
+  k_stash<<<dim3((unsigned)((n + 255) / 256), S.B), 256, 0, st>>>(S);
+}
+void launch_vprep(const Batch &S, cudaStream_t st) { k_vprep<<<(S.NO + 127) / 128, 128, 0, st>>>(S); }
+void launch_output(const Batch &S, const double *kgrid, int v0, int nv, cudaStream_t st) {
+  k_output<<<dim3((S.nk + 127) / 128, nv), 128, 0, st>>>(S, kgrid, v0);
+}
+// device-side loop condition of rtrg_run's conditional (while) graph node
+__global__ void k_loop_cond(cudaGraphConditionalHandle handle, const int *n_active, long long *rounds,
+                            long long max_rounds) {
+  const long long r = ++(*rounds);
+  cudaGraphSetConditional(handle, (*n_active > 0 && r < max_rounds) ? 1u : 0u);
+}
+void launch_loop_cond(unsigned long long handle, const Batch &S, long long max_rounds, cudaStream_t st) {
+  k_loop_cond<<<1, 1, 0, st>>>((cudaGraphConditionalHandle)handle, S.n_active, S.rounds, max_rounds);
 }
 
 }  // namespace rtrg

@@ -30,7 +30,8 @@ enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55 };
 #define RTRG_NKERN_DEFINED
 enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
 #endif
-enum { BIL_R = 8 };  // output rows per CTA of the bilinear kernel
+enum { BIL_R = 8 };      // output rows per row block of the bilinear kernel
+enum { BIL_TPB = 384 };  // its threads per CTA
 // output groups of one evaluation of the mode-coupling integrals
 enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15, GRP_RAW = 16 };
 enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
@@ -42,7 +43,8 @@ struct IntegralTabs {
   int LP;      // padded length of one reversed spectrum (even)
   int NUp;     // rows of the compact kernel table (>= nk + NVp)
   int ldT;     // leading dimension of the compact kernel table
-  int nchunk;  // CTAs along the alpha-side lag dimension
+  int nchunk;  // partial sums per row block: the most CTAs along the item axis one row block spans
+  int tpb;     // threads per CTA of the bilinear kernel (BIL_TPB)
   int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
@@ -102,6 +104,20 @@ struct Batch {
   long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
   int *act, *nact;         // [B], [1] compacted list of the cosmologies of the current launch
   int *n_active;           // [1]
+  long long *rounds;       // [1] rounds executed by the device-side loop of rtrg_run
+  // deferred outputs: the round loop only stashes the state at every output redshift; the
+  // 1-loop output integrals (rt:1646-1653) and the tables are then produced for all NO =
+  // sum n_out (cosmology, output) pairs ("virtual cosmologies") in a few large launches
+  int NO;
+  double *ystash;          // [NO][41][nk]
+  double *t_stash;         // [NO] eta reached when the output was taken
+  int *vbase;              // [B] first virtual index of cosmology b
+  int *vc_b, *vc_io;       // [NO] cosmology and output index of virtual cosmology v
+  int *vc_have;            // [NO] stashed in this run
+  int *vc_mask;            // [NO] needs the output integrals
+  Cosmo *cosmo_v;          // [NO] copy of cosmo[vc_b[v]] (the integral kernels index it by v)
+  long long *matvecs_v;    // [NO]
+  double *src_v;           // [VCH][55][nk] sources of one chunk of virtual cosmologies
   // outputs
   double *out;             // concatenated tables
   long long *out_off;      // [B] offset of cosmology b in out

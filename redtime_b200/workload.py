@@ -39,12 +39,38 @@ def extract_example1(dst):
     return dst
 
 
-def load_example1(subsample=1):
-    """The example-1 inputs as the dict RedTimeB200.add_cosmology takes (parsed by the
-    library's own C++ reader).  subsample > 1 keeps every subsample-th table row."""
-    from .binding import read_run_dir
+def read_run_dir_numpy(path):
+    """params_redTime.dat + the 7-column CAMB files it names, parsed with numpy alone (the layout of
+    hdr:231-353, 547-627, 790-832).  Used where the product library must not be loaded: the
+    reference arm of bench.py.  Same dict as redtime_b200.read_run_dir (tests/test_host_io.py)."""
+    with open(os.path.join(path, "params_redTime.dat")) as f:
+        tok = [l.split("#")[0].strip() for l in f if l.split("#")[0].strip()]
+    params = np.array([float(t.split()[0]) for t in tok[:9]])
+    switches = [int(t.split()[0]) for t in tok[9:13]]
+    z_in, n_out = float(tok[13].split()[0]), int(tok[14].split()[0])
+    z_out = np.array([float(x) for x in tok[15].split()[:n_out]])
+    tfile, root, n_z = tok[16].split()[0], tok[18].split()[0], int(tok[19].split()[0])
+    zs = tok[20].split()[:n_z]
+    t0 = np.loadtxt(os.path.join(path, tfile), usecols=(0, 1, 2))
+    tabs = [np.loadtxt(os.path.join(path, "%s%s.dat" % (root, z)), usecols=(0, 1, 5)) for z in zs]
+    return dict(params=params, switches=switches, z_in=z_in, z_out=z_out,
+                k_T=np.ascontiguousarray(t0[:, 0]), Tc_T=np.ascontiguousarray(t0[:, 1]),
+                Tb_T=np.ascontiguousarray(t0[:, 2]), z_interp=np.array([float(z) for z in zs]),
+                k_b=np.ascontiguousarray(tabs[0][:, 0]) if tabs else np.zeros(0),
+                Tc_b=np.array([t[:, 1] for t in tabs]) if tabs else np.zeros((0, 0)),
+                Tnu_b=np.array([t[:, 2] for t in tabs]) if tabs else np.zeros((0, 0)))
+
+
+def load_example1(subsample=1, use_library=True):
+    """The example-1 inputs as the dict RedTimeB200.add_cosmology takes, parsed by the library's
+    own C++ reader (use_library=False: by numpy, without loading the library).  subsample > 1
+    keeps every subsample-th table row."""
     with tempfile.TemporaryDirectory() as tmp:
-        d = read_run_dir(extract_example1(tmp))
+        if use_library:
+            from .binding import read_run_dir
+            d = read_run_dir(extract_example1(tmp))
+        else:
+            d = read_run_dir_numpy(extract_example1(tmp))
     if subsample > 1:
         sl = slice(None, None, subsample)
         for key in ("k_T", "Tc_T", "Tb_T", "k_b"):
@@ -71,11 +97,14 @@ def _pinned_like(a):
     return v
 
 
-def make_cosmologies(n, base, seed=SEED, switches=(1, 1, 1, 1), z_out=REDSHIFTS_CE, z_in=200.0, pinned=False):
+def make_cosmologies(n, base, seed=SEED, switches=(1, 1, 1, 1), z_out=REDSHIFTS_CE, z_in=200.0, pinned=False,
+                     total=None):
     """n cosmologies (list of add_cosmology dicts) sharing base's table shapes.  pinned=True puts
     every table in page-locked host memory (needs a CUDA device): the library then sends them to
-    the GPU without a host-side copy."""
-    u, eps = latin_hypercube(n, seed)
+    the GPU without a host-side copy.  total: size of the Latin-hypercube draw the n cosmologies are
+    the FIRST n members of (a Latin hypercube depends on its size) -- this is how the CPU reference
+    runs a sample of exactly the cosmologies of a larger GPU batch."""
+    u, eps = latin_hypercube(total if total else n, seed)
     out = []
     if pinned:
         base = dict(base)

@@ -38,6 +38,10 @@ def main():
     ap.add_argument("--lib", default=None)
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--light", action="store_true", help="skip the raw J/PZ arrays")
+    ap.add_argument("--floor", type=int, default=0, metavar="N",
+                    help="only measure the round-off floor of the assembled integrals (SURVEY H2): N "
+                         "evaluations of compute_*_full on yp with ln P moved by a random -1/0/+1 ulp; "
+                         "writes floor_{A,R,PT,PMR} = max |difference to the unperturbed result|")
     a = ap.parse_args()
     here = os.path.dirname(os.path.abspath(__file__))
     lib_path = a.lib or os.path.join(here, "..", "oracle", "_ref", "libredtime_stage.so")
@@ -74,6 +78,26 @@ def main():
     ref.ref_extrap_P.argtypes = [dp, dp]
     ref.ref_compute_full.argtypes = [C.c_double, dp, dp, dp, dp, dp]
     ref.ref_derivatives.argtypes = [C.c_double, dp, dp]
+    if a.floor > 0:
+        # the assembled integrals are cancelling sums of FFT-built J's (redTime.cc:1182-1184);
+        # their round-off floor is what the reference itself moves by when its input moves by one ulp
+        def full(y):
+            o = [np.zeros(64 * nk), np.zeros(24 * nk), np.zeros(9 * nk), np.zeros(8 * nk)]
+            ref.ref_compute_full(0.0, P(y), *[P(x) for x in o])
+            return [x.reshape(-1, nk) for x in o]
+        base = full(yp)
+        fl = [np.zeros_like(x) for x in base]
+        rng = np.random.default_rng(a.seed + 1)
+        for _ in range(a.floor):
+            y = yp.copy()
+            d = rng.integers(-1, 2, size=3 * nk)
+            y[:3 * nk] = np.where(d > 0, np.nextafter(y[:3 * nk], np.inf),
+                                  np.where(d < 0, np.nextafter(y[:3 * nk], -np.inf), y[:3 * nk]))
+            for f, x, b in zip(fl, full(y), base):
+                np.maximum(f, np.abs(x - b), out=f)
+        os.dup2(saved, 1)
+        np.savez_compressed(out_path, k=k, floor_A=fl[0], floor_R=fl[1], floor_PT=fl[2], floor_PMR=fl[3])
+        return 0
     for tag, y in (("y0", y0), ("yp", yp)):
         P3 = np.zeros(3 * npad)
         ref.ref_extrap_P(P(y), P(P3))
