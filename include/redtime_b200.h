@@ -132,6 +132,30 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
 int rtrg_fetch_outputs(rtrg_handle *h, const double **out, size_t *out_len, const double **hdr,
                        const double **hdr0);
 
+/* ---- double-buffered batch pipeline (what replaces the sequential model loop of
+ * scripts/runRedTimeBatch:91-99) -----------------------------------------------------------
+ * `depth` handles on cfg->device (2 = double buffering) behind two worker threads: while batch i
+ * evolves (rtrg_run + rtrg_fetch_outputs on the run thread), batch i+1 is staged, uploaded and
+ * initialised (rtrg_add_cosmologies + rtrg_prepare on the stage thread), so host staging and the
+ * PCIe transfers hide behind the GPU time of the previous batch.  Results are bit-identical to the
+ * serial add / prepare / run sequence.
+ *   submit : returns at once with a ticket; the caller's tables (and the list array's entries)
+ *            must stay valid and unchanged until rtrg_pipeline_wait(ticket) has returned
+ *   wait   : blocks until the batch is done; out / hdr / hdr0 (layouts as in rtrg_run) point into
+ *            page-locked memory of the pipeline and status[n] holds the per-cosmology status;
+ *            all stay valid until rtrg_pipeline_release(ticket).  Returns the batch's error code
+ *   release: frees the batch's slot for a later submission (at most `depth` unreleased batches
+ *            are in flight; further submissions queue)                                      */
+typedef struct rtrg_pipeline rtrg_pipeline;
+int rtrg_pipeline_create(const rtrg_config *cfg, int depth, rtrg_pipeline **out);
+int rtrg_pipeline_submit(rtrg_pipeline *p, int n, const rtrg_cosmology *const *list, long long *ticket);
+int rtrg_pipeline_wait(rtrg_pipeline *p, long long ticket, const double **out, size_t *out_len,
+                       const double **hdr, const double **hdr0, const int **status);
+/* columns of cosmology i of a finished batch (rtrg_num_columns) */
+int rtrg_pipeline_columns(rtrg_pipeline *p, long long ticket, int icosmo);
+int rtrg_pipeline_release(rtrg_pipeline *p, long long ticket);
+int rtrg_pipeline_destroy(rtrg_pipeline *p);
+
 /* ---- one high-resolution cosmology sharded over its k-rows ---------------
  * Create one handle per rank with cfg.k_shards = number of ranks and cfg.k_rank = this rank
  * (nk/8 must be divisible by k_shards), add the SAME cosmologies to each, attach a transport,
@@ -145,6 +169,8 @@ int rtrg_fetch_outputs(rtrg_handle *h, const double **out, size_t *out_len, cons
  *              blocks move with peer copies (single-GPU testing, or NVLink P2P without NCCL). */
 int rtrg_kshard_nccl_id(char id[128]);
 int rtrg_kshard_init_nccl(rtrg_handle *h, const char id[128]);
+/* description of the transport attached to the handle ("none" without one) */
+const char *rtrg_kshard_transport(const rtrg_handle *h);
 typedef struct rtrg_loopback rtrg_loopback;
 int rtrg_kshard_loopback_create(int nranks, rtrg_loopback **out);
 int rtrg_kshard_init_loopback(rtrg_handle *h, rtrg_loopback *g);

@@ -250,6 +250,74 @@ def pack_cosmologies(dicts):
     return PackedCosmologies(dicts)
 
 
+class Pipeline:
+    """rtrg_pipeline_*: double-buffered batches on one GPU (staging/upload/initialisation of batch
+    i+1 overlap the evolution of batch i).  submit() takes PackedCosmologies (kept alive until the
+    batch has been waited for) and returns a ticket; wait() returns (tables, hdr, hdr0, status) as
+    views of page-locked memory that stay valid until release()."""
+
+    def __init__(self, depth=2, **kw):
+        lib = load_library()
+        self.lib = lib
+        self.cfg = Config()
+        lib.rtrg_default_config(C.byref(self.cfg))
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError("unknown config field %r" % k)
+            setattr(self.cfg, k, v)
+        lib.rtrg_pipeline_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
+        lib.rtrg_pipeline_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(_Cosmology)),
+                                             C.POINTER(C.c_longlong)]
+        lib.rtrg_pipeline_wait.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(_dp), C.POINTER(C.c_size_t),
+                                           C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_ip)]
+        lib.rtrg_pipeline_columns.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+        lib.rtrg_pipeline_release.argtypes = [C.c_void_p, C.c_longlong]
+        lib.rtrg_pipeline_destroy.argtypes = [C.c_void_p]
+        self.p = C.c_void_p()
+        _check(lib.rtrg_pipeline_create(C.byref(self.cfg), int(depth), C.byref(self.p)))
+        self.nk = self.cfg.nk
+        self._jobs = {}
+
+    def submit(self, packed):
+        if not isinstance(packed, PackedCosmologies):
+            packed = PackedCosmologies(packed)
+        t = C.c_longlong()
+        _check(self.lib.rtrg_pipeline_submit(self.p, len(packed.structs), packed.array, C.byref(t)))
+        self._jobs[t.value] = packed
+        return t.value
+
+    def wait(self, ticket, raise_on_failure=True):
+        packed = self._jobs[ticket]
+        po, ph, ph0, ps, n = _dp(), _dp(), _dp(), _ip(), C.c_size_t()
+        rc = self.lib.rtrg_pipeline_wait(self.p, ticket, C.byref(po), C.byref(n), C.byref(ph), C.byref(ph0),
+                                         C.byref(ps))
+        if rc != 0 and raise_on_failure:
+            _check(rc)
+        B = len(packed.structs)
+        out = np.ctypeslib.as_array(po, shape=(n.value,))
+        hdr = np.ctypeslib.as_array(ph, shape=(B, MAX_OUT, 5))
+        hdr0 = np.ctypeslib.as_array(ph0, shape=(B, 2))
+        status = np.ctypeslib.as_array(ps, shape=(B,))
+        tables, o = [], 0
+        for i in range(B):
+            ncols = self.lib.rtrg_pipeline_columns(self.p, ticket, i)
+            sz = packed.n_out[i] * self.nk * ncols
+            tables.append(out[o:o + sz].reshape(packed.n_out[i], self.nk, ncols))
+            o += sz
+        return tables, hdr, hdr0, status
+
+    def release(self, ticket):
+        _check(self.lib.rtrg_pipeline_release(self.p, ticket))
+        self._jobs.pop(ticket, None)
+
+    def close(self):
+        if getattr(self, "p", None) and self.p:
+            self.lib.rtrg_pipeline_destroy(self.p)
+            self.p = None
+
+    __del__ = close
+
+
 def dfma_peak_tflops(device=0, seconds=0.5):
     """Measured FP64 FMA peak of the device (TFLOP/s)."""
     lib = load_library()
@@ -366,6 +434,22 @@ class RedTimeB200:
 
     def kshard_init_nccl(self, unique_id):
         _check(self.lib.rtrg_kshard_init_nccl(self.h, unique_id))
+
+    def kshard_init_auto(self, dist):
+        """k-shard transport for one process per GPU under torch.distributed: rank 0's NCCL unique id
+        travels through the process group; returns a description of the transport in use."""
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if dist.get_rank() == 0:
+            idt.copy_(torch.frombuffer(bytearray(kshard_nccl_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        self.kshard_init_nccl(bytes(idt.cpu().numpy().tobytes()))
+        return self.kshard_transport()
+
+    def kshard_transport(self):
+        self.lib.rtrg_kshard_transport.restype = C.c_char_p
+        self.lib.rtrg_kshard_transport.argtypes = [C.c_void_p]
+        return self.lib.rtrg_kshard_transport(self.h).decode()
 
     def kshard_init_loopback(self, group):
         _check(self.lib.rtrg_kshard_init_loopback(self.h, group.g))

@@ -4,8 +4,12 @@ working on the in-memory tables rtrg_run returns instead of re-reading text file
 * convert_pt  -- src/convert_pt.c:124-184: pick one output redshift, go from h-units to physical
   units (k [h/Mpc] -> k h [1/Mpc], P [(Mpc/h)^3] -> P / h^3) and rescale the non-linear P_cb by
   f_cb^2 = ((Omega_m - Omega_nu) / Omega_m)^2 (the delta_cb vs delta_m convention of the N-body
-  spectra, src/convert_pt.c:51-55); also returns D normalised to its last wavenumber's value at
-  z = 0 and the neutrino spectrum, as process_PT_runs does.
+  spectra, src/convert_pt.c:51-55); also returns D divided by its value at the LAST wavenumber of
+  the SAME redshift block (src/convert_pt.c:173: D0 = D_h[nk_pt*(output_z+1)-1]) and the neutrino
+  spectrum, as process_PT_runs does.  The file-level drop-in for the tool itself is the C++
+  executable redtime_b200/convertPt_b200 (csrc/convert_pt_main.cc), pinned byte for byte on the
+  reference's own source in tests/test_convert_pt.py; this function is the same arithmetic on the
+  in-memory tables.
 * emulator_delta2 -- tests/emulator_comparison/test_models.py:20-40: the dimensionless
   Delta^2-like quantity P k^1.5 / (2 pi^2 h^3) the regression compares, without and with the
   neutrino correction f^2 = (1 - f_nu + beta_P)^2 rebuilt from columns 4 and 7.
@@ -23,7 +27,7 @@ def convert_pt(table, h, omega_m, omega_nu, i_out=-1):
     t = np.asarray(table)
     f_cb = (omega_m - omega_nu) / omega_m
     blk = t[i_out]
-    D0 = t[-1, -1, COL_D]                      # D of the last row of the last (z = 0) block
+    D0 = blk[-1, COL_D]                        # D at the last wavenumber of this block (convert_pt.c:173)
     return dict(k=blk[:, COL_K] * h,
                 pk=blk[:, COL_PNL] / h ** 3 * f_cb ** 2,
                 D=blk[:, COL_D] / D0,

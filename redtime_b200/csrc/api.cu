@@ -31,6 +31,7 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
                         const int *mask, cudaStream_t st);
 int integrals_configure(const IntegralTabs &tb);
 size_t bilinear_smem_bytes(const IntegralTabs &tb);
+int bilinear_tpb();
 // kernels_linear.cu
 int linear_upload_constants();
 int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof);
@@ -80,11 +81,18 @@ static int fail(int code, const char *fmt, ...) {
 struct HostCosmo {
   Cosmo c;  // offsets point into the device input pool
   std::vector<double> z_out;
-  size_t stage_off = 0, stage_len = 0;  // slice of the staging arena = slice of the pool at c.offT
-  // page-locked interpolation tables are sent as they are (no host copy): T_nu, T_c
-  bool direct = false;
-  size_t big_len = 0;
-  const double *src[2] = {nullptr, nullptr};
+  // what the host copies into the staging arena: slice [stage_off, stage_off + stage_len) of the
+  // arena = slice of the pool at pool_off
+  size_t stage_off = 0, stage_len = 0, pool_off = 0;
+  // page-locked caller tables are sent as they are (no host copy): up to 6 direct segments
+  // k_T, Tc_T, Tb_T, k_b and the raw interpolation tables T_nu, T_c
+  int n_direct = 0;
+  size_t direct_len = 0;
+  const double *dsrc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t dlen[6] = {0, 0, 0, 0, 0, 0};
+  long long doff[6] = {0, 0, 0, 0, 0, 0};
+  bool small_direct = false;  // k_T, Tc_T, Tb_T, k_b go out directly
+  bool direct = false;        // T_nu, T_c go out directly (beta is formed on the device)
 };
 
 // Pinned host arena mirroring the device input pool: rtrg_add_cosmology copies the caller's
@@ -384,8 +392,8 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   tb.LP = tb.NVp + BIL_R;
   tb.NUp = nk - BIL_R + tb.NVp;
   tb.ldT = (nk + g.nsup - 1 + 7) / 8 * 8;
-  tb.tpb = BIL_TPB;
-  tb.nchunk = (tb.NV + BIL_TPB - 2) / BIL_TPB + 1;
+  tb.tpb = bilinear_tpb();
+  tb.nchunk = (tb.NV + tb.tpb - 2) / tb.tpb + 1;
   tb.vsplit = cfg->v_split;
   tb.dlnk = g.dlnk;
   {
@@ -611,10 +619,10 @@ static bool is_page_locked(const void *p) {
   }
   return at.type == cudaMemoryTypeHost;
 }
-// Scalars + layout of one cosmology.  Its "small" tables (k_T, Tc_T, Tb_T, a, k_b -- and beta
-// when it is formed on the host) start at device-pool offset `off` = staging-arena offset `soff`
-// region; the two big raw tables of a direct cosmology (T_nu, T_c of the interpolation files)
-// are placed by the caller afterwards (place_big).
+// Scalars + layout of one cosmology.  The part the host copies (a nodes; the small tables k_T,
+// Tc_T, Tb_T, k_b unless they are page-locked; beta or its pre-reduction) starts at arena offset
+// `soff` = pool offset `off`; page-locked caller tables are sent directly and are placed by the
+// caller afterwards (place_direct).
 static HostCosmo describe_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, size_t off, size_t soff) {
   HostCosmo hc;
   Cosmo &c = hc.c;
@@ -630,59 +638,99 @@ static HostCosmo describe_cosmology(const rtrg_handle *h, const rtrg_cosmology *
   c.n_z = in->n_z > 0 ? in->n_z : 0;
   c.n_kb = c.n_z > 0 ? in->n_kb : 0;
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
-  c.offT = (long long)off;
-  c.offLT = (long long)(off + nT);
-  c.offTb = (long long)(off + 2 * nT);
-  c.offA = (long long)(off + 3 * nT);
-  c.offKb = (long long)(off + 3 * nT + nz);
-  c.offB = (long long)(off + 3 * nT + nz + nkb);
+  hc.stage_off = soff;
+  hc.pool_off = off;
+  hc.small_direct = is_page_locked(in->k_T) && is_page_locked(in->Tc_T) && is_page_locked(in->Tb_T) &&
+                    (nz == 0 || is_page_locked(in->k_b));
+  size_t o = off;
+  if (hc.small_direct) {
+    hc.dsrc[0] = in->k_T, hc.dlen[0] = nT;
+    hc.dsrc[1] = in->Tc_T, hc.dlen[1] = nT;
+    hc.dsrc[2] = in->Tb_T, hc.dlen[2] = nT;
+    hc.dsrc[3] = in->k_b, hc.dlen[3] = nkb;
+    hc.n_direct = nz ? 4 : 3;
+  } else {
+    c.offT = (long long)o, c.offLT = (long long)(o + nT), c.offTb = (long long)(o + 2 * nT);
+    o += 3 * nT;
+  }
+  c.offA = (long long)o;
+  o += nz;
+  if (!hc.small_direct) {
+    c.offKb = (long long)o;
+    o += nkb;
+  }
+  c.offB = (long long)o;
   c.offTc = -1;
   c.offRow1 = c.offBred = -1;
-  hc.stage_off = soff;
   if (h->cfg.reduce_beta && nz > 0) {
     // only what the run consumes: beta(a=1, k_b) and beta at the nkk slot wavenumbers
     const size_t nkk = h->slot_k.size();
     c.offRow1 = c.offB;
     c.offBred = c.offB + (long long)nkb;
-    hc.stage_len = 3 * nT + nz + nkb + nkb + nz * nkk;
-    return hc;
+    o += nkb + nz * nkk;
+  } else {
+    hc.direct = nz > 0 && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b);
+    if (hc.direct) {
+      hc.dsrc[hc.n_direct] = in->Tnu_b, hc.dlen[hc.n_direct++] = nz * nkb;
+      hc.dsrc[hc.n_direct] = in->Tc_b, hc.dlen[hc.n_direct++] = nz * nkb;
+    } else {
+      o += nz * nkb;
+    }
   }
-  hc.direct = nz > 0 && is_page_locked(in->Tc_b) && is_page_locked(in->Tnu_b);
-  hc.stage_len = 3 * nT + nz + nkb + (hc.direct ? 0 : nz * nkb);
-  hc.big_len = hc.direct ? 2 * nz * nkb : 0;
-  if (hc.direct) hc.src[0] = in->Tnu_b, hc.src[1] = in->Tc_b;
+  hc.stage_len = o - off;
+  for (int i = 0; i < hc.n_direct; i++) hc.direct_len += hc.dlen[i];
   return hc;
 }
-static void place_big(HostCosmo &hc, size_t off_big) {
-  if (!hc.direct) return;
-  hc.c.offB = (long long)off_big;
-  hc.c.offTc = (long long)(off_big + (size_t)hc.c.n_z * hc.c.n_kb);
+// pool offsets of the direct segments, starting at off_direct
+static void place_direct(HostCosmo &hc, size_t off_direct) {
+  Cosmo &c = hc.c;
+  size_t o = off_direct;
+  int i = 0;
+  if (hc.small_direct) {
+    hc.doff[0] = c.offT = (long long)o, o += hc.dlen[0];
+    hc.doff[1] = c.offLT = (long long)o, o += hc.dlen[1];
+    hc.doff[2] = c.offTb = (long long)o, o += hc.dlen[2];
+    i = 3;
+    if (c.n_z > 0) hc.doff[3] = c.offKb = (long long)o, o += hc.dlen[3], i = 4;
+  }
+  if (hc.direct) {
+    hc.doff[i] = c.offB = (long long)o, o += hc.dlen[i], i++;
+    hc.doff[i] = c.offTc = (long long)o, o += hc.dlen[i], i++;
+  }
 }
-// copy the caller's small tables into the staging arena; pageable interpolation tables are
+// copy what the host has to touch into the staging arena; pageable interpolation tables are
 // reduced to beta = f_nu T_nu / T_c on the way (hdr:556-623), which halves their PCIe bytes
 static void stage_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, const HostCosmo &hc, double *base) {
   const Cosmo &c = hc.c;
   const size_t nT = c.nT, nz = c.n_z, nkb = c.n_kb;
   double *s = base + hc.stage_off;
-  std::memcpy(s, in->k_T, nT * sizeof(double));
-  std::memcpy(s + nT, in->Tc_T, nT * sizeof(double));
-  std::memcpy(s + 2 * nT, in->Tb_T, nT * sizeof(double));
-  for (size_t i = 0; i < nz; i++) s[3 * nT + i] = 1.0 / (1.0 + in->z_interp[i]);
-  if (nz) std::memcpy(s + 3 * nT + nz, in->k_b, nkb * sizeof(double));
+  if (!hc.small_direct) {
+    std::memcpy(s, in->k_T, nT * sizeof(double));
+    std::memcpy(s + nT, in->Tc_T, nT * sizeof(double));
+    std::memcpy(s + 2 * nT, in->Tb_T, nT * sizeof(double));
+    s += 3 * nT;
+  }
+  double *a_nodes = s;
+  for (size_t i = 0; i < nz; i++) s[i] = 1.0 / (1.0 + in->z_interp[i]);
+  s += nz;
+  if (nz && !hc.small_direct) {
+    std::memcpy(s, in->k_b, nkb * sizeof(double));
+    s += nkb;
+  }
   if (nz && c.offRow1 >= 0) {
     // pre-reduction of the beta table: the 2-D rule interpolates in a first, column
     // by column, and then in k (tab:262-328), so (i) the row at a = 1 and (ii) the k-stencil
     // applied to every a row are all the run needs.  Same arithmetic as beta_P / k_beta_reduce.
     const double fn = c.On / c.Om;
-    const double *tn = in->Tnu_b, *tc = in->Tc_b, *a = s + 3 * nT, *kb = in->k_b;
+    const double *tn = in->Tnu_b, *tc = in->Tc_b, *a = a_nodes, *kb = in->k_b;
     auto beta = [&](size_t j, size_t i) { return fn * tn[j * nkb + i] / tc[j * nkb + i]; };
-    double *row1 = s + 3 * nT + nz + nkb, *bred = row1 + nkb;
+    double *row1 = s, *bred = row1 + nkb;
     const int X = (int)nz, nx = tab_find(a, X, 1.0);
-    for (size_t i = 0; i < nkb; i++) {
-      if (nx > 0 && nx < X - 2)
+    if (nx > 0 && nx < X - 2) {
+      for (size_t i = 0; i < nkb; i++)
         row1[i] = cub4(a + nx - 1, beta(nx - 1, i), beta(nx, i), beta(nx + 1, i), beta(nx + 2, i), 1.0);
-      else
-        row1[i] = lin2(a[nx], a[nx + 1], beta(nx, i), beta(nx + 1, i), 1.0);
+    } else {
+      for (size_t i = 0; i < nkb; i++) row1[i] = lin2(a[nx], a[nx + 1], beta(nx, i), beta(nx + 1, i), 1.0);
     }
     const size_t nkk = h->slot_k.size();
     for (size_t kk = 0; kk < nkk; kk++) {
@@ -699,36 +747,35 @@ static void stage_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, cons
   if (nz && !hc.direct) {
     const double fn = c.On / c.Om;
     const double *tn = in->Tnu_b, *tc = in->Tc_b;
-    double *dst = s + 3 * nT + nz + nkb;
     const size_t n = nz * nkb;
-    for (size_t i = 0; i < n; i++) dst[i] = fn * tn[i] / tc[i];
+    for (size_t i = 0; i < n; i++) s[i] = fn * tn[i] / tc[i];
   }
 }
-// host -> device copies of the big raw tables of one direct cosmology, straight from the
-// caller's page-locked buffers
-static int upload_big(rtrg_handle *h, const HostCosmo &hc) {
-  if (!hc.direct) return RTRG_OK;
-  const size_t n = (size_t)hc.c.n_z * hc.c.n_kb * sizeof(double);
-  CU(cudaMemcpyAsync(h->d_in + hc.c.offB, hc.src[0], n, cudaMemcpyHostToDevice, h->copy_stream));
-  CU(cudaMemcpyAsync(h->d_in + hc.c.offTc, hc.src[1], n, cudaMemcpyHostToDevice, h->copy_stream));
+// host -> device copies of the direct segments of one cosmology, straight from the caller's
+// page-locked buffers
+static int upload_direct(rtrg_handle *h, const HostCosmo &hc) {
+  for (int i = 0; i < hc.n_direct; i++)
+    if (hc.dlen[i])
+      CU(cudaMemcpyAsync(h->d_in + hc.doff[i], hc.dsrc[i], hc.dlen[i] * sizeof(double), cudaMemcpyHostToDevice,
+                         h->copy_stream));
   return RTRG_OK;
 }
 // (re-)send everything of the cosmologies [b0, b1)
 static int upload_range(rtrg_handle *h, size_t b0, size_t b1) {
   if (b0 >= b1) return RTRG_OK;
-  // small tables: each add call left one contiguous slice in the arena and in the pool
+  // staged parts: each add call left one contiguous slice in the arena and in the pool
   size_t i = b0;
   while (i < b1) {
     size_t j = i, len = 0;
-    while (j < b1 && h->cos[j].c.offT == h->cos[i].c.offT + (long long)len &&
-           h->cos[j].stage_off == h->cos[i].stage_off + len)
+    while (j < b1 && h->cos[j].pool_off == h->cos[i].pool_off + len && h->cos[j].stage_off == h->cos[i].stage_off + len)
       len += h->cos[j++].stage_len;
-    CU(cudaMemcpyAsync(h->d_in + h->cos[i].c.offT, h->stage.base + h->cos[i].stage_off, len * sizeof(double),
-                       cudaMemcpyHostToDevice, h->copy_stream));
+    if (len)
+      CU(cudaMemcpyAsync(h->d_in + h->cos[i].pool_off, h->stage.base + h->cos[i].stage_off, len * sizeof(double),
+                         cudaMemcpyHostToDevice, h->copy_stream));
     i = j;
   }
   for (size_t b = b0; b < b1; b++) {
-    int rc = upload_big(h, h->cos[b]);
+    int rc = upload_direct(h, h->cos[b]);
     if (rc) return rc;
   }
   return RTRG_OK;
@@ -757,10 +804,14 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
     soff += h->cos.back().stage_len;
   }
   for (int i = 0; i < n; i++) {
-    place_big(h->cos[first + i], off);
-    off += h->cos[first + i].big_len;
+    place_direct(h->cos[first + i], off);
+    off += h->cos[first + i].direct_len;
   }
-  if (soff > h->stage.cap) CU(cudaStreamSynchronize(h->copy_stream));  // the arena is about to move
+  h->prepared = h->uploaded = false;
+  if (soff > h->stage.cap && cudaStreamSynchronize(h->copy_stream) != cudaSuccess) {  // the arena is about to move
+    roll_back();
+    return fail(RTRG_ECUDA, "cudaStreamSynchronize(copy stream): %s", cudaGetErrorString(cudaGetLastError()));
+  }
   if (h->stage.reserve(soff) != RTRG_OK) {
     roll_back();
     return fail(RTRG_ENOMEM, "pinned staging arena of %zu bytes", soff * sizeof(double));
@@ -768,7 +819,10 @@ int rtrg_add_cosmologies(rtrg_handle *h, int n, const rtrg_cosmology *const *lis
   h->stage.used = soff;
   h->d_in_used = off;
   if (h->d_in_used > h->d_in_cap) {
-    CU(cudaStreamSynchronize(h->copy_stream));
+    if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) {
+      roll_back();
+      return fail(RTRG_ECUDA, "cudaStreamSynchronize(copy stream): %s", cudaGetErrorString(cudaGetLastError()));
+    }
     double *q = nullptr;
     const size_t ncap = h->d_in_used + h->d_in_used / 8;
     cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(double));
@@ -1092,6 +1146,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   CU(cudaMemcpyAsync(S.n_active, &n_active, sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(S.rounds, 0, sizeof(long long), st));
   CU(cudaMemsetAsync(S.vc_have, 0, S.NO * sizeof(int), st));
+  CU(cudaMemsetAsync(S.hdr, 0, (size_t)B * MAX_OUT * 5 * sizeof(double), st));  // a = 0 marks "never produced"
 
   // --- k-sharded mode: all-gather of the ranks' ln P rows, max-reduction of the error norm
   const bool sharded = h->cfg.k_shards > 1;
@@ -1367,6 +1422,7 @@ int rtrg_kshard_init_nccl(rtrg_handle *h, const char id[128]) {
   if (!h->xch) return fail(RTRG_ECUDA, "%s", err.c_str());
   return RTRG_OK;
 }
+const char *rtrg_kshard_transport(const rtrg_handle *h) { return (h && h->xch) ? h->xch->name() : "none"; }
 struct rtrg_loopback {
   std::shared_ptr<LoopbackGroup> g;
 };

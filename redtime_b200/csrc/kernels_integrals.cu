@@ -162,21 +162,22 @@ __global__ void k_compact(const int *__restrict__ mask, int B, int *__restrict__
 // Work distribution.  A row block (R consecutive output rows) needs one thread per alpha-side lag,
 // NV = nsup + R - 1 of them (334 at nk = 128), each streaming its own column of the shifted T_n
 // window.  The (row block, lag) pairs of ALL row blocks are laid out on one axis, item = rb NV + tu,
-// and cut into CTAs of TPB = 384 consecutive items: 12 full warps per CTA, 24 per SM -- every lane
-// of every warp owns a lag (16 row blocks x 334 lags fill 13.92 CTAs, the 14th is 92 % full) and
-// the four schedulers of an SM hold six warps each.  (One CTA per row block left 18 of its 352
-// threads idle and spread 22 warps 6/6/6/4.)  A CTA therefore touches up to three row blocks; this
+// and cut into CTAs of TPB = 256 consecutive items: 8 full warps per CTA, three CTAs = 24 warps per
+// SM at 80 registers -- every lane of every warp owns a lag (16 row blocks x 334 lags fill 20.9
+// CTAs) and the four schedulers of an SM hold six warps each.  (One CTA per row block left 18 of
+// its 352 threads idle and spread 22 warps 6/6/6/4: 68.5 % of the DFMA peak; this layout reaches
+// 73.3 %, 72.4 % with 384-thread CTAs -- tools/ab_bilinear.sh.)  A CTA touches up to three row blocks; this
 // costs nothing inside the main loop because the beta-side windows do not depend on the row block
 // (T_n is shifted along its diagonal, the spectra are not), and the epilogue reduces the lags of
 // each row block separately.  The item axis is global (independent of k-sharding), so a sharded
 // run adds the same numbers in the same order as the unsharded one.
 // Grid: (CTAs along the item axis x v_split, items of the launch, slot triples).
-template <int R, int TPB, int VC>
-__global__ void __launch_bounds__(TPB, 2)
+template <int R, int TPB, int VC, int NS, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
                double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
                const int *__restrict__ act, const int *__restrict__ nact) {
-  constexpr int NS = 3, NWARP = TPB / 32;
+  constexpr int NWARP = TPB / 32, NSL = 3 * NS;  // NSL: (slot, ab) sums per row
   const BilItem item = L.it[blockIdx.y];
   const int n = item.n, ncd = item.ncd;
   const int nslots = (*nact) * ncd;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(TPB, 2)
   const int c = c_lo + cx;
   extern __shared__ __align__(128) double sm[];
   double *s_a = sm;                     // [NS][3][LP]: the three spectra of each slot's cosmology
-  double *s_red = sm + NS * 3 * tb.LP;  // [NWARP][2][9R]
+  double *s_red = sm + NS * 3 * tb.LP;  // [NWARP][2][NSL R]
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int s_wrb[NWARP][2];       // row block(s) the lanes of each warp belong to
   __shared__ int s_e[NS], s_cd[NS], s_ok[NS];
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(TPB, 2)
           prod[r] = m * acc[r][q];
         }
         warp_sum_multi<R>(prod, lane);
-        if ((lane & 3) == 0) s_red[(warp * 2 + side) * (9 * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
+        if ((lane & 3) == 0) s_red[(warp * 2 + side) * (NSL * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
       }
     }
   }
@@ -308,8 +309,8 @@ __global__ void __launch_bounds__(TPB, 2)
   // order and store this CTA's part of the row block
   const int rb_first = (c * TPB) / tb.NV, nrbl = (c * TPB + TPB - 1) / tb.NV - rb_first + 1;
   const int nch = tb.nchunk * tb.vsplit;
-  for (int idx = tid; idx < nrbl * 9 * R; idx += TPB) {
-    const int rbl = idx / (9 * R), x = idx - rbl * (9 * R), rbx = rb_first + rbl;
+  for (int idx = tid; idx < nrbl * NSL * R; idx += TPB) {
+    const int rbl = idx / (NSL * R), x = idx - rbl * (NSL * R), rbx = rb_first + rbl;
     if (rbx < rb_lo || rbx >= rb_hi) continue;
     const int slot = x / R, r = x - slot * R, q = slot / 3, ab = slot - 3 * q;
     const int e = s_e[q];
@@ -318,8 +319,8 @@ __global__ void __launch_bounds__(TPB, 2)
     double s = 0.0;
 #pragma unroll 1
     for (int wv = 0; wv < NWARP; wv++) {
-      if (s_wrb[wv][0] == rbx) s += s_red[(wv * 2) * (9 * R) + x];
-      if (s_wrb[wv][1] == rbx) s += s_red[(wv * 2 + 1) * (9 * R) + x];
+      if (s_wrb[wv][0] == rbx) s += s_red[(wv * 2) * (NSL * R) + x];
+      if (s_wrb[wv][1] == rbx) s += s_red[(wv * 2 + 1) * (NSL * R) + x];
     }
     const int part = vs * tb.nchunk + (c - (rbx * tb.NV) / TPB);
     double *dst = Jpart + (((long long)e * N_JKERN + n) * nch + part) * 9 * tb.nk + rbx * R + r;
@@ -460,8 +461,39 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------- launchers
+// Tuning variants of the bilinear kernel (threads per CTA, slots per CTA, CTAs per SM), selected
+// once per process by RTRG_BIL_VARIANT; 0 is the production configuration (256 threads, 3 slots,
+// 3 CTAs per SM).  Results do not
+// depend on the slot count; they depend on the threads per CTA at round-off level (which lags
+// share a partial sum).
+struct BilVariant {
+  int tpb, ns;
+};
+static const BilVariant kBilVariants[] = {{256, 3}, {320, 3}, {256, 3}, {384, 2}, {256, 4}, {320, 4}, {384, 3}};
+static int bil_variant_index() {
+  static const int v = [] {
+    const char *e = std::getenv("RTRG_BIL_VARIANT");
+    const int i = e ? std::atoi(e) : 0;
+    return (i >= 0 && i < (int)(sizeof kBilVariants / sizeof kBilVariants[0])) ? i : 0;
+  }();
+  return v;
+}
+int bilinear_tpb() { return kBilVariants[bil_variant_index()].tpb; }
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
-  return (size_t)(9 * tb.LP + (BIL_TPB / 32) * 2 * 9 * BIL_R) * sizeof(double);
+  const BilVariant v = kBilVariants[bil_variant_index()];
+  return (size_t)(3 * v.ns * tb.LP + (v.tpb / 32) * 2 * 3 * v.ns * BIL_R) * sizeof(double);
+}
+template <class F>
+static auto bil_dispatch(F &&f) {
+  switch (bil_variant_index()) {
+    case 1: return f(k_bilinear<BIL_R, 320, 8, 3, 2>, 320, 3);
+    case 2: return f(k_bilinear<BIL_R, 256, 8, 3, 2>, 256, 3);
+    case 3: return f(k_bilinear<BIL_R, 384, 8, 2, 2>, 384, 2);
+    case 4: return f(k_bilinear<BIL_R, 256, 8, 4, 2>, 256, 4);
+    case 5: return f(k_bilinear<BIL_R, 320, 8, 4, 2>, 320, 4);
+    case 6: return f(k_bilinear<BIL_R, 384, 8, 3, 2>, 384, 3);
+    default: return f(k_bilinear<BIL_R, 256, 8, 3, 3>, 256, 3);
+  }
 }
 
 // Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
@@ -509,10 +541,12 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     for (int i = 0; i < nitems; i++) maxncd = std::max(maxncd, (int)L.it[i].ncd);
     // CTAs along the global (row block, lag) axis that hold lags of this rank's row blocks
     const int rb_lo = row0 / BIL_R, rb_hi = (row0 + nrows) / BIL_R;
-    const int c_lo = (rb_lo * tb.NV) / BIL_TPB, c_hi = (rb_hi * tb.NV - 1) / BIL_TPB;
-    dim3 g((c_hi - c_lo + 1) * tb.vsplit, nitems, (B * maxncd + 2) / 3);
-    k_bilinear<BIL_R, BIL_TPB, 8><<<g, BIL_TPB, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo,
-                                                                             rb_hi, c_lo, S.act, S.nact);
+    bil_dispatch([&](auto kern, int tpb, int ns) {
+      const int c_lo = (rb_lo * tb.NV) / tpb, c_hi = (rb_hi * tb.NV - 1) / tpb;
+      dim3 g((c_hi - c_lo + 1) * tb.vsplit, nitems, (B * maxncd + ns - 1) / ns);
+      kern<<<g, tpb, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo, rb_hi, c_lo, S.act, S.nact);
+      return 0;
+    });
     launches++;
   }
   RT_TOC(prof, st);
@@ -554,8 +588,9 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 
 int integrals_configure(const IntegralTabs &tb) {
   // opt in to the dynamic shared memory the bilinear kernel needs on large grids
-  return (int)cudaFuncSetAttribute(k_bilinear<BIL_R, BIL_TPB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)bilinear_smem_bytes(tb));
+  return bil_dispatch([&](auto kern, int, int) {
+    return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bilinear_smem_bytes(tb));
+  });
 }
 
 }  // namespace rtrg

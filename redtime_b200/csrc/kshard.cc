@@ -68,6 +68,7 @@ class NcclExchange : public Exchange {
   int nranks() const override { return nranks_; }
   int rank() const override { return rank_; }
   bool capturable() const override { return true; }
+  const char *name() const override { return "NCCL all-gather / all-reduce per exchange"; }
   int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) override {
     ncclResult_t r = api_->GroupStart();
     for (const Segment &s : segs) {
@@ -157,6 +158,7 @@ class LoopbackExchange : public Exchange {
   int nranks() const override { return g_->n; }
   int rank() const override { return rank_; }
   bool capturable() const override { return false; }  // host-side rendezvous between the ranks
+  const char *name() const override { return "in-process loopback (peer copies, host rendezvous)"; }
   int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) override {
     // my block must be complete before anybody reads it
     if (cudaStreamSynchronize(st) != cudaSuccess) return fail(err);

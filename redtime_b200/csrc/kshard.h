@@ -33,6 +33,7 @@ class Exchange {
   // true when the exchange consists of plain kernel / memcpy nodes only, so that it may sit in the
   // body of a conditional (while) graph node
   virtual bool device_side() const { return false; }
+  virtual const char *name() const = 0;
   // in-place all-gather of every segment, ordered on `st`; returns 0 or sets err
   virtual int allgather(const std::vector<Segment> &segs, cudaStream_t st, std::string *err) = 0;
   // in-place max over ranks of n unsigned 64-bit values (bit patterns of non-negative doubles)

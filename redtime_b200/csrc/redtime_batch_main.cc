@@ -93,15 +93,26 @@ int main(int argc, char **argv) {
     while (d.size() > 1 && d.back() == '/') d.pop_back();
     const std::string model = d.substr(d.rfind('/') == std::string::npos ? 0 : d.rfind('/') + 1);
     const std::string path = d + "/redTime_" + model + ".dat";
-    FILE *f = std::fopen(path.c_str(), "w");
-    if (!f) {
-      std::fprintf(stderr, "redTimeBatch_b200: cannot write %s\n", path.c_str());
-      failed++;
+    const double *hd = hdr + (size_t)i * RTRG_MAX_OUT * 5;
+    if (status[i] == 101 || status[i] == 103) {
+      // the reference abort()s on these (hdr:528-531, 646-649): no table, and no stale one either
+      std::remove(path.c_str());
+      std::fprintf(stderr, "redTimeBatch_b200: %s: status %d, no table written\n", d.c_str(), status[i]);
     } else {
-      if (status[i]) std::fprintf(f, "#WARNING: integrator failed, status = %d\n", status[i]);  // rt:1631-1632
-      rtrg_print_result(f, "params_redTime.dat", cfg.nk, ncols, n_out, out + off, hdr + (size_t)i * RTRG_MAX_OUT * 5,
-                        hdr0 + 2 * (size_t)i);
-      std::fclose(f);
+      FILE *f = std::fopen(path.c_str(), "w");
+      if (!f) {
+        std::fprintf(stderr, "redTimeBatch_b200: cannot write %s\n", path.c_str());
+        if (!status[i]) failed++;
+      } else {
+        int n_done = n_out;
+        if (status[i]) {  // integrator failure: the outputs reached, then the warning (rt:1631-1632)
+          n_done = 0;
+          while (n_done < n_out && hd[(size_t)n_done * 5 + 1] != 0.0) n_done++;
+        }
+        if (n_done > 0) rtrg_print_result(f, "params_redTime.dat", cfg.nk, ncols, n_done, out + off, hd, hdr0 + 2 * (size_t)i);
+        if (status[i]) std::fprintf(f, "#WARNING: integrator failed, status = %d\n", status[i]);
+        std::fclose(f);
+      }
     }
     if (status[i]) failed++;
     off += (size_t)n_out * cfg.nk * ncols;

@@ -56,9 +56,32 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "redTime_b200: %s\n", rtrg_last_error());
     return 3;
   }
-  if (status) std::printf("#WARNING: integrator failed, status = %d\n", status);  // rt:1631-1632
-  rtrg_print_result(stdout, nullptr, cfg.nk, ncols, c->n_out, out.data(), hdr.data(), hdr0.data());
+  // A cosmology outside the reference's table ranges (status 103) or whose sigma_8 integral failed
+  // (101) makes the reference abort() (hdr:528-531, 646-649): no table, non-zero exit.  An
+  // integrator failure (102) prints the warning where the reference does (rt:1631-1632), after the
+  // outputs reached before it, and still exits non-zero so that `redTime_b200 > out.dat` pipelines
+  // never take a truncated table for a result.
+  if (status == 101 || status == 103) {
+    std::fprintf(stderr, "redTime_b200: %s (status %d): the reference aborts here; no table written\n",
+                 status == 103 ? "look-up outside the D_dD / Beta_P table ranges" : "sigma_8 normalisation integral failed",
+                 status);
+    rtrg_destroy(h);
+    rtrg_free_run_inputs(in);
+    return 4;
+  }
+  int n_done = c->n_out;
+  if (status) {
+    n_done = 0;
+    while (n_done < c->n_out && hdr[(size_t)n_done * 5 + 1] != 0.0) n_done++;  // a = 0: never produced
+  }
+  if (n_done > 0)
+    rtrg_print_result(stdout, nullptr, cfg.nk, ncols, n_done, out.data(), hdr.data(), hdr0.data());
+  if (status) {
+    std::printf("#WARNING: integrator failed, status = %d\n", status);
+    std::fflush(stdout);
+    std::fprintf(stderr, "redTime_b200: integrator failed after %d of %d outputs\n", n_done, c->n_out);
+  }
   rtrg_destroy(h);
   rtrg_free_run_inputs(in);
-  return 0;
+  return status ? 5 : 0;
 }

@@ -31,7 +31,6 @@ enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55 };
 enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
 #endif
 enum { BIL_R = 8 };      // output rows per row block of the bilinear kernel
-enum { BIL_TPB = 384 };  // its threads per CTA
 // output groups of one evaluation of the mode-coupling integrals
 enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15, GRP_RAW = 16 };
 enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
@@ -44,7 +43,7 @@ struct IntegralTabs {
   int NUp;     // rows of the compact kernel table (>= nk + NVp)
   int ldT;     // leading dimension of the compact kernel table
   int nchunk;  // partial sums per row block: the most CTAs along the item axis one row block spans
-  int tpb;     // threads per CTA of the bilinear kernel (BIL_TPB)
+  int tpb;     // threads per CTA of the bilinear kernel
   int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR

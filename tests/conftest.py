@@ -110,3 +110,97 @@ def stage_golden_1loop(example1_dir):
 @pytest.fixture(scope="session")
 def stage_golden_full(example1_full_dir):
     return load_or_make_stage_golden("example1_stage_full", example1_full_dir)
+
+
+# ---------------------------------------------------------------------------------------------
+# parity assertions with the MEASURED round-off floor of the reference
+# ---------------------------------------------------------------------------------------------
+def load_floor(tag):
+    """floor[z, k, col] = how far the reference's own table moves when sigma_8 or n_s moves by one
+    ulp (tests/golden/make_floor.py): the cancellation noise of redTime.cc:1182-1184 & co."""
+    return np.asarray(np.load(os.path.join(GOLDEN, "floor_tables.npz"))[tag], dtype=float)
+
+
+def smooth_floor(floor):
+    """A handful of perturbed runs samples the noise, it does not bound it: widen every entry to the
+    max over the redshifts and over the row's two neighbours in k."""
+    f = np.max(floor, axis=0, keepdims=True) * np.ones_like(floor)
+    g = f.copy()
+    g[:, 1:] = np.maximum(g[:, 1:], f[:, :-1])
+    g[:, :-1] = np.maximum(g[:, :-1], f[:, 1:])
+    return g
+
+
+def local_scale(ref):
+    """max |ref| over the row and its two neighbours on either side: the bispectrum columns P_B,j(k)
+    change sign (e.g. at k = 0.095 h/Mpc), where a plain relative error measures the distance to
+    the zero crossing rather than the accuracy."""
+    a = np.abs(ref)
+    scale = a.copy()
+    for sh in (1, 2):
+        scale[:, sh:] = np.maximum(scale[:, sh:], a[:, :-sh])
+        scale[:, :-sh] = np.maximum(scale[:, :-sh], a[:, sh:])
+    return scale
+
+
+FLOOR_C = 5.0  # multiple of the measured floor allowed on top of the relative tolerance
+
+
+def table_excess(tab, ref, floor, c=FLOOR_C, tol_hi=1e-5):
+    """Per column: max over (z, k) of |tab - ref| / allowed, with the north-star tolerances
+        columns 1-7   : 1e-6 |ref|
+        columns 8-10  : 1e-5 |ref|
+        columns 11-.. : 1e-5 local_scale(ref) + c floor(z, k, col)      -- at EVERY k
+    A value <= 1 passes."""
+    d = np.abs(tab - ref)
+    allowed = np.empty_like(d)
+    allowed[..., :7] = 1e-6 * np.abs(ref[..., :7])
+    allowed[..., 7:10] = 1e-5 * np.abs(ref[..., 7:10])
+    allowed[..., 10:] = tol_hi * local_scale(ref)[..., 10:] + c * smooth_floor(floor)[..., 10:]
+    return np.max(d / (allowed + 1e-300), axis=(0, 1))
+
+
+def assert_table_parity(tab, ref, floor, c=FLOOR_C, tol_hi=1e-5, what=""):
+    assert tab.shape == ref.shape, (tab.shape, ref.shape)
+    ex = table_excess(tab, ref, floor, c, tol_hi)
+    assert np.all(ex <= 1.0), (what, np.round(ex, 3))
+    return ex
+
+
+def oracle_tables_with_floor(dirs, binary="redTime", threads_total=None):
+    """Run the oracle binary on every run directory AND on two copies with sigma_8 / n_s moved by
+    one ulp (all processes concurrently, one OpenMP thread each unless few): returns
+    [(hdr_lines, table[n_out*nk, ncols], floor like the table)] -- the on-the-spot version of
+    make_floor.py for cosmologies that have no committed floor fixture."""
+    import tempfile
+    jobs = []
+    tmp = tempfile.mkdtemp(prefix="rtfloor")
+    for i, d in enumerate(dirs):
+        variants = [d]
+        for j, (line, sgn) in enumerate(((1, +1), (0, -1))):
+            dd = os.path.join(tmp, "c%d_p%d" % (i, j))
+            shutil.copytree(d, dd)
+            p = os.path.join(dd, "params_redTime.dat")
+            src = open(p).read().split("\n")
+            vals = [n for n, l in enumerate(src) if l.strip() and not l.startswith("#")]
+            x = float(src[vals[line]].split()[0])
+            src[vals[line]] = "%.17g" % np.nextafter(x, np.inf if sgn > 0 else -np.inf)
+            open(p, "w").write("\n".join(src))
+            variants.append(dd)
+        jobs.append(variants)
+    n_proc = sum(len(v) for v in jobs)
+    ncpu = threads_total or os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(max(1, ncpu // n_proc)))
+    procs = [[subprocess.Popen([os.path.join(ORACLE_REF, binary)], cwd=v, env=env, stdout=subprocess.PIPE)
+              for v in variants] for variants in jobs]
+    out = []
+    for ps in procs:
+        txt = [p.communicate()[0].decode() for p in ps]
+        assert all(p.returncode == 0 for p in ps)
+        hdr, base = parse_tables(txt[0])
+        fl = np.zeros_like(base)
+        for t in txt[1:]:
+            np.maximum(fl, np.abs(parse_tables(t)[1] - base), out=fl)
+        out.append((hdr, base, fl))
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import redtime_b200 as rt
-from conftest import GOLDEN, parse_tables
+from conftest import GOLDEN, parse_tables, load_floor, assert_table_parity, local_scale, smooth_floor, FLOOR_C
 
 pytestmark = pytest.mark.gpu
 NK = 128
@@ -47,22 +47,14 @@ def test_example1_1loop(example1_dir, golden_example1):
     assert tab.shape == (7, NK, 17)
     # the step sequence genuine GSL took
     assert (cnt["attempts"], cnt["rejected"]) == (23, 4)
-    k = gold[0, :, 0]
-    for ref in (gold, orc):
-        e = col_err(tab, ref)
-        assert np.all(e[:7] < 1e-6), e      # columns 1-7
-        assert np.all(e[7:15] < 1e-5), e    # columns 8-15 at every k
-        hi = k > 3.3e-3
-        assert np.all(col_err(tab[:, hi], ref[:, hi])[15:] < 1e-5), e
-    # Columns 16-17 (P_T,6, P_T,8) below k = 3.3e-3 h/Mpc are 1e3..1e9-fold cancellations of the
-    # J integrals: there the reference linked to genuine GSL and the same sources linked to a
-    # different FFT (the oracle) already disagree by up to 8e-2.  Bound our
-    # distance to the oracle by that measured floor: 1e-5 + 5 x (floor of the row and its
-    # neighbours, max over redshifts).
-    rel_go = np.max(np.abs(gold - orc) / (np.abs(orc) + 1e-300), axis=0)  # [k, col]
-    rel_to = np.max(np.abs(tab - orc) / (np.abs(orc) + 1e-300), axis=0)
-    floor = np.maximum(rel_go, np.maximum(np.roll(rel_go, 1, axis=0), np.roll(rel_go, -1, axis=0)))
-    assert np.all(rel_to[:, 15:] <= 1e-5 + 5 * floor[:, 15:]), rel_to[:24, 15:]
+    # North-star tolerances at EVERY k: 1e-6 (columns 1-7), 1e-5 (8-10), and for the mode-coupling
+    # columns 11-17 1e-5 of the local scale + 5 x the reference's own round-off floor, measured by
+    # moving sigma_8 / n_s by one ulp (tests/golden/make_floor.py; SURVEY H2: columns 16-17 are
+    # 1e3..1e9-fold cancellations of the J integrals below k = 3e-3 h/Mpc, rt:1182-1184).  The
+    # genuine-GSL golden carries the noise of a different FFT as well: 8 x the floor there.
+    floor = load_floor("1loop")
+    assert_table_parity(tab, orc, floor, what="vs oracle")
+    assert_table_parity(tab, gold, floor, c=8.0, what="vs genuine-GSL golden")
 
 
 def test_example1_header_lines(example1_dir, golden_example1, tmp_path):
@@ -79,10 +71,7 @@ def test_example1_full_trg(example1_full_dir):
     assert status == 0
     _, orc = load_oracle("full")
     orc = orc.reshape(7, NK, 17)
-    e = col_err(tab, orc)
-    assert np.all(e[:7] < 1e-6), e
-    assert np.all(e[7:10] < 1e-5), e
-    assert np.all(e[10:13] < 1e-5), e
+    assert_table_parity(tab, orc, load_floor("full"), what="full Time-RG vs oracle")
     assert not tab[:, :, 13:].any()  # columns 14-17 are zeros in full-TRG mode
 
 
@@ -203,7 +192,7 @@ def test_reduced_beta_upload(example1_dir, example1_full_dir):
     """reduce_beta = 1: the host sends beta(a=1,k) and the table pre-reduced in k instead of the
     full Beta_P(a,k) table.  Same interpolation rules in the other order: results
     agree to round-off (host code has no FMA contraction, the device code has)."""
-    for d in (example1_dir, example1_full_dir):
+    for d, tag in ((example1_dir, "1loop"), (example1_full_dir, "full")):
         full, hdr_f, hdr0_f, _, cnt_f = run(d)
         red, hdr_r, hdr0_r, _, cnt_r = run(d, reduce_beta=1)
         assert cnt_f == cnt_r
@@ -211,10 +200,10 @@ def test_reduced_beta_upload(example1_dir, example1_full_dir):
         # full Time-RG right-hand side: measured 1.2e-10 on columns 8-10 (1-loop mode: < 1e-13)
         assert np.max(np.abs(red[:, :, :7] - full[:, :, :7]) / np.abs(full[:, :, :7]).clip(1e-300)) < 1e-12
         assert np.max(np.abs(red[:, :, 7:10] - full[:, :, 7:10]) / np.abs(full[:, :, 7:10])) < 2e-9
-        # columns 11-17 amplify a 1-ulp change of the inputs by up to 1e8 at the lowest k (SURVEY
-        # H2/V9: the reference's own round-off floor); compare them above k = 5.7e-3 h/Mpc
-        hi = full[0, :, 0] > 5.7e-3
-        assert np.max(np.abs(red[:, hi] - full[:, hi]) / (np.abs(full[:, hi]) + 1e-300)) < 1e-6  # measured 1.6e-7
+        # columns 11-17 amplify a 1-ulp change of the inputs by up to 1e8 at the lowest k: bounded at
+        # every k by 1e-6 of the local scale + the reference's measured response to a 1-ulp change
+        allowed = 1e-6 * local_scale(full) + FLOOR_C * smooth_floor(load_floor(tag))
+        assert np.all(np.abs(red - full)[:, :, 10:] <= allowed[:, :, 10:])
         assert np.allclose(hdr_r[:7], hdr_f[:7], rtol=1e-13, atol=0) and np.allclose(hdr0_r, hdr0_f, rtol=1e-13, atol=0)
     h = rt.RedTimeB200(reduce_beta=1)
     h.add_cosmology(rt.read_run_dir(example1_dir))
