@@ -179,6 +179,12 @@ void rtrg_kshard_loopback_free(rtrg_loopback *g);
 /* Work counters of the last rtrg_run for cosmology i:
  * counters[0]=RKF45 attempts, [1]=rejected, [2]=RHS evaluations, [3]=integral evaluations */
 int rtrg_counters(const rtrg_handle *h, int icosmo, long long counters[4]);
+/* Error norms rmax = max_i |yerr_i| / (eps_rel |y_i| + eps_abs) of the first (up to 128) RKF45
+ * attempts of cosmology i in the last rtrg_run, in order; returns how many were written (<= cap).
+ * GSL's controller rejects an attempt when rmax > 1.1 (gsl odeiv control.c: std_control_hadjust,
+ * driven from src/redTime.cc:1616): an rmax within round-off of 1.1 marks a cosmology whose step
+ * sequence -- and with it P(k) at the 1e-4 level -- flips under 1-ulp changes of the inputs.   */
+int rtrg_rmax_history(rtrg_handle *h, int icosmo, double *out, int cap);
 /* (kernel, beta-side spectrum) matrix-vector sets k_bilinear executed for cosmology i since the
  * last rtrg_device_init, up to the end of the last rtrg_run; one set = nk rows x (2 nsup^2 +
  * 6 nsup) FLOP.  Only the products the requested outputs consume are computed.            */
@@ -254,6 +260,9 @@ void rtrg_free_run_inputs(rtrg_run_inputs *in);
  * src/redTime.cc:1602-1603,1639-1641,1670-1741; banner line of hdr:236) */
 int rtrg_print_result(void *cfile, const char *paramfile_name, int nk, int ncols, int n_out,
                       const double *out, const double *hdr, const double *hdr0);
+
+/* the printer's number format, "%20.12g", for n values: dst receives 20 n characters + NUL */
+int rtrg_format_g12(const double *v, int n, char *dst);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,10 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libredtime_b200.so")
+    """The in-tree product library; RTRG_LIBRARY selects another in-tree build of it (the debug
+    build with device-side bounds asserts, libredtime_b200_bounds.so)."""
+    name = os.environ.get("RTRG_LIBRARY", "libredtime_b200.so")
+    return name if os.path.isabs(name) else os.path.join(_HERE, os.path.basename(name))
 
 
 def load_library():
@@ -511,6 +514,15 @@ class RedTimeB200:
         c = (C.c_longlong * 4)()
         _check(self.lib.rtrg_counters(self.h, i, c))
         return dict(attempts=c[0], rejected=c[1], rhs=c[2], integral_evals=c[3])
+
+    def rmax_history(self, i=0):
+        """Error norms of the RKF45 attempts of cosmology i in the last run (rtrg_rmax_history)."""
+        buf = np.zeros(128)
+        self.lib.rtrg_rmax_history.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        n = self.lib.rtrg_rmax_history(self.h, i, _P(buf), 128)
+        if n < 0:
+            _check(n)
+        return buf[:n].copy()
 
     def matvec_sets(self, i=0):
         return int(self.lib.rtrg_matvec_sets(self.h, i))

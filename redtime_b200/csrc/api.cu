@@ -169,6 +169,7 @@ struct rtrg_handle {
   int *d_hookmask = nullptr, *d_err = nullptr, *d_minit = nullptr;
   size_t scratch_len = 0;
   std::unique_ptr<Exchange> xch;  // k-shard transport (k_shards > 1)
+  GatherPlan plan_lnP, plan_out;  // what the ranks exchange: ln P rows of a state vector, output rows
   Profiler profiler;
   Profiler *prof = nullptr;  // &profiler when profiling is switched on
   double prof_ms[PC_NCAT] = {0};
@@ -210,10 +211,15 @@ static void prof_collect(rtrg_handle *h) {
 // nk=256).  Building them takes ~1.3 s (5 s) of long-double FFTs on the host; the drop-in
 // executable is started once per model, so it reloads them instead.  RTRG_CACHE_DIR selects the
 // directory (default $XDG_CACHE_HOME/redtime_b200 or ~/.cache/redtime_b200; "off" disables).
+// Bump TABLE_CACHE_VERSION whenever build_T (fastpt_tables.cc), the packing below (Tc layout,
+// BIL_R, the lag window) or this header changes: a file written by an older build is then rebuilt
+// instead of trusted.
+enum { TABLE_CACHE_VERSION = 3 };
 struct TableCacheHeader {
   char magic[8];
-  int version, nk, np, nsup, n_tc, n_tlo, n_kfac, pad;
-  double kmin, kmax, kfac_lo, checksum;
+  int version, nk, np, nsup, n_tc, n_tlo, n_kfac, bil_r;
+  double kmin, kmax, kfac_lo;
+  unsigned long long checksum;  // FNV-1a over every byte of the three arrays
 };
 static std::string table_cache_path(const GridSpec &g) {
   const char *dir = std::getenv("RTRG_CACHE_DIR");
@@ -229,14 +235,21 @@ static std::string table_cache_path(const GridSpec &g) {
     return "";
   }
   char name[160];
-  std::snprintf(name, sizeof name, "/T_v2_nk%d_%.17g_%.17g.bin", g.nk, g.kmin, g.kmax);
+  std::snprintf(name, sizeof name, "/T_v%d_nk%d_%.17g_%.17g.bin", (int)TABLE_CACHE_VERSION, g.nk, g.kmin, g.kmax);
   return d + name;
 }
-static double table_checksum(const std::vector<double> &a, const std::vector<double> &b, const std::vector<double> &c) {
-  double s = 0;
-  for (const auto *v : {&a, &b, &c})
-    for (size_t i = 0; i < v->size(); i += 97) s += (*v)[i] * (double)(1 + i % 13);
-  return s;
+static unsigned long long table_checksum(const std::vector<double> &a, const std::vector<double> &b,
+                                         const std::vector<double> &c) {
+  // FNV-1a, 64 bit, over all bytes, eight at a time (the arrays are doubles)
+  unsigned long long hsh = 1469598103934665603ULL;
+  for (const auto *v : {&a, &b, &c}) {
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(v->data());
+    for (size_t i = 0; i < v->size(); i++) {
+      hsh ^= w[i];
+      hsh *= 1099511628211ULL;
+    }
+  }
+  return hsh;
 }
 static bool load_table_cache(const std::string &path, const GridSpec &g, std::vector<double> &Tc,
                              std::vector<double> &Tlo, std::vector<double> &kfac, double *kfac_lo) {
@@ -244,8 +257,8 @@ static bool load_table_cache(const std::string &path, const GridSpec &g, std::ve
   FILE *f = std::fopen(path.c_str(), "rb");
   if (!f) return false;
   TableCacheHeader h;
-  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTRGTAB", 8) == 0 && h.version == 2 &&
-            h.nk == g.nk && h.np == g.np && h.nsup == g.nsup && h.kmin == g.kmin && h.kmax == g.kmax &&
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "RTRGTAB", 8) == 0 && h.version == TABLE_CACHE_VERSION &&
+            h.bil_r == BIL_R && h.nk == g.nk && h.np == g.np && h.nsup == g.nsup && h.kmin == g.kmin && h.kmax == g.kmax &&
             (size_t)h.n_tc == Tc.size() && (size_t)h.n_tlo == Tlo.size() && (size_t)h.n_kfac == kfac.size();
   ok = ok && std::fread(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size();
   ok = ok && std::fread(Tlo.data(), sizeof(double), Tlo.size(), f) == Tlo.size();
@@ -268,7 +281,7 @@ static void save_table_cache(const std::string &path, const GridSpec &g, const s
   TableCacheHeader h;
   std::memset(&h, 0, sizeof h);
   std::memcpy(h.magic, "RTRGTAB", 8);
-  h.version = 2, h.nk = g.nk, h.np = g.np, h.nsup = g.nsup;
+  h.version = TABLE_CACHE_VERSION, h.bil_r = BIL_R, h.nk = g.nk, h.np = g.np, h.nsup = g.nsup;
   h.n_tc = (int)Tc.size(), h.n_tlo = (int)Tlo.size(), h.n_kfac = (int)kfac.size();
   h.kmin = g.kmin, h.kmax = g.kmax, h.kfac_lo = kfac_lo, h.checksum = table_checksum(Tc, Tlo, kfac);
   bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(Tc.data(), sizeof(double), Tc.size(), f) == Tc.size() &&
@@ -521,6 +534,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
 
   int rc = 0;
   auto &P = h->table_allocs;
+  tb.n_Tc = (long long)Tc.size();
   rc = rc ? rc : dev_upload(P, &tb.Tc, Tc);
   rc = rc ? rc : dev_upload(P, &tb.Tlo, Tlo);
   rc = rc ? rc : dev_upload(P, &tb.kfac, kfac);
@@ -875,6 +889,8 @@ int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *in) { return rtrg_a
 int rtrg_prepare(rtrg_handle *h) {
   if (!h) return fail(RTRG_EINVAL, "null handle");
   if (h->cos.empty()) return fail(RTRG_EINVAL, "no cosmologies");
+  if (h->cos.size() > 65535)  // the batch index is a grid y/z dimension of the kernels
+    return fail(RTRG_EINVAL, "%zu cosmologies in one batch; the limit is 65535 (split the batch)", h->cos.size());
   CU(cudaSetDevice(h->cfg.device));
   free_pool(h->batch_allocs);  // hook scratch buffers of the previous batch
   h->prepared = h->uploaded = false;
@@ -959,6 +975,33 @@ int rtrg_prepare(rtrg_handle *h) {
   const size_t NE = (size_t)B * N_U * nk, ng = (size_t)(cfg.n_lna + 1) * (cfg.n_lnk + 1);
   const IntegralTabs &tb = h->tb;
   double *d_lna = nullptr, *d_lnkg = nullptr;
+  // k-sharding: segment tables of the two gathers.  [0] the three ln P components of a state vector
+  // (segment = one component of one cosmology, nk doubles, rank r owns rows [r nk/G, (r+1) nk/G));
+  // [1] the output tables (segment = the nk x ncols block of one output, rank r owns its rows)
+  const bool sharded_cfg = cfg.k_shards > 1;
+  std::vector<long long> plan_off[2], plan_pre[2];
+  std::vector<int> plan_len[2];
+  long long plan_total[2] = {0, 0};
+  if (sharded_cfg) {
+    for (int b = 0; b < B; b++)
+      for (int c = 0; c < N_UP; c++) {
+        plan_off[0].push_back(((long long)b * N_U + c) * nk);
+        plan_len[0].push_back(rows_per);
+      }
+    for (int b = 0; b < B; b++)
+      for (int io = 0; io < h->cos[b].c.n_out; io++) {
+        plan_off[1].push_back(h->out_off[b] + (long long)io * nk * h->ncols[b]);
+        plan_len[1].push_back(rows_per * h->ncols[b]);
+      }
+    for (int p = 0; p < 2; p++)
+      for (int l : plan_len[p]) {
+        plan_pre[p].push_back(plan_total[p]);
+        plan_total[p] += l;
+      }
+  }
+  const size_t n_seg[2] = {plan_off[0].size(), plan_off[1].size()};
+  long long *d_plan_off[2] = {nullptr, nullptr}, *d_plan_pre[2] = {nullptr, nullptr};
+  int *d_plan_len[2] = {nullptr, nullptr};
   auto carve = [&](DeviceArena &A) {
     A.used = 0;
     S.cosmo = A.take<Cosmo>(B);
@@ -1009,6 +1052,7 @@ int rtrg_prepare(rtrg_handle *h) {
     S.m_loc_step = A.take<int>(B);
     S.att_time = A.take<double>((size_t)B * RK_STAGES * 48);  // RhsShared is < 48 doubles
     S.counters = A.take<long long>((size_t)4 * B);
+    S.rmax_hist = A.take<double>((size_t)B * RMAX_HIST);
     S.matvecs = A.take<long long>(B);
     S.act = A.take<int>(BV);
     S.nact = A.take<int>(1);
@@ -1024,6 +1068,9 @@ int rtrg_prepare(rtrg_handle *h) {
     S.cosmo_v = A.take<Cosmo>(S.NO);
     S.matvecs_v = A.take<long long>(S.NO);
     S.src_v = A.take<double>((size_t)h->vch * N_SRC * nk);
+    // k-shard gather plans (segment tables)
+    d_plan_off[0] = A.take<long long>(n_seg[0]), d_plan_len[0] = A.take<int>(n_seg[0]), d_plan_pre[0] = A.take<long long>(n_seg[0]);
+    d_plan_off[1] = A.take<long long>(n_seg[1]), d_plan_len[1] = A.take<int>(n_seg[1]), d_plan_pre[1] = A.take<long long>(n_seg[1]);
     S.out = A.take<double>(h->out_total);
     S.hdr = A.take<double>((size_t)B * MAX_OUT * 5);
     S.hdr0 = A.take<double>((size_t)B * 2);
@@ -1067,6 +1114,9 @@ int rtrg_prepare(rtrg_handle *h) {
   CU(cudaStreamWaitEvent(st, h->copy_done, 0));
   h->d_in_transformed = true;
   S.in = h->d_in;
+  S.n_in = (long long)h->d_in_used;
+  S.n_out_total = (long long)h->out_total;
+  S.n_slots = (long long)BV;
   CU(cudaMemcpyAsync(S.cosmo, cs.data(), B * sizeof(Cosmo), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.zout, zout.data(), zout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.aout, aout.data(), aout.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1078,6 +1128,21 @@ int rtrg_prepare(rtrg_handle *h) {
   CU(cudaMemcpyAsync(S.vbase, vbase.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.vc_b, vc_b.data(), vc_b.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(S.vc_io, vc_io.data(), vc_io.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (sharded_cfg) {
+    for (int p = 0; p < 2; p++) {
+      CU(cudaMemcpyAsync(d_plan_off[p], plan_off[p].data(), n_seg[p] * sizeof(long long), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_plan_len[p], plan_len[p].data(), n_seg[p] * sizeof(int), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_plan_pre[p], plan_pre[p].data(), n_seg[p] * sizeof(long long), cudaMemcpyHostToDevice, st));
+      GatherPlan &gp = p ? h->plan_out : h->plan_lnP;
+      gp.nseg = (int)n_seg[p], gp.total = plan_total[p];
+      gp.off = d_plan_off[p], gp.len = d_plan_len[p], gp.prefix = d_plan_pre[p];
+    }
+    if (h->xch) {
+      std::string xerr;
+      if (h->xch->reserve(std::max(plan_total[0], plan_total[1]), (size_t)B, &xerr) != 0)
+        return fail(RTRG_ENOMEM, "%s", xerr.c_str());
+    }
+  }
   h->launches += launch_prep_inputs(S, h->d_T0, max_rows, st, h->prof);
   CU(cudaStreamSynchronize(st));  // the host vectors above go out of scope
   h->uploaded = true;
@@ -1152,18 +1217,17 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   const bool sharded = h->cfg.k_shards > 1;
   if (sharded && (!h->xch || h->xch->nranks() != h->cfg.k_shards || h->xch->rank() != h->cfg.k_rank))
     return fail(RTRG_EINVAL, "k_shards > 1 needs rtrg_kshard_init_nccl() or rtrg_kshard_init_loopback()");
-  const size_t rows_bytes = (size_t)(S.k_hi - S.k_lo) * sizeof(double);
   std::string xerr;
-  auto gather_lnP = [&](double *yv) -> int {
-    if (!sharded) return 0;
-    std::vector<Segment> segs;
-    for (int b = 0; b < B; b++)
-      for (int c = 0; c < N_UP; c++) segs.push_back({yv + ((size_t)b * N_U + c) * nk, rows_bytes});
-    return h->xch->allgather(segs, st, &xerr);
-  };
+  if (sharded && h->xch->reserve(std::max(h->plan_lnP.total, h->plan_out.total), (size_t)B, &xerr) != 0)
+    return fail(RTRG_ENOMEM, "%s", xerr.c_str());
+  auto gather_lnP = [&](double *yv) -> int { return sharded ? h->xch->gather(yv, h->plan_lnP, true, st, &xerr) : 0; };
+  // a rank that leaves with an error wakes the ranks that would wait for it (loopback transport)
 #define XCH(call)                                                             \
   do {                                                                        \
-    if ((call) != 0) return fail(RTRG_ECUDA, "k-shard exchange: %s", xerr.c_str()); \
+    if ((call) != 0) {                                                        \
+      h->xch->abort();                                                        \
+      return fail(RTRG_ECUDA, "k-shard exchange: %s", xerr.c_str());          \
+    }                                                                         \
   } while (0)
 
   // --- dydt_in of the first step
@@ -1330,13 +1394,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     }
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, v0, nv, st));
   }
-  if (sharded) {  // every rank ends up with the complete tables
-    std::vector<Segment> segs;
-    for (int b = 0; b < B; b++)
-      for (int io = 0; io < h->cos[b].c.n_out; io++)
-        segs.push_back({S.out + h->out_off[b] + (size_t)io * nk * h->ncols[b], rows_bytes * h->ncols[b]});
-    XCH(h->xch->allgather(segs, st, &xerr));
-  }
+  if (sharded) XCH(h->xch->gather(S.out, h->plan_out, false, st, &xerr));  // every rank ends up with the complete tables
 #undef XCH
 
   if (out) CU(cudaMemcpyAsync(out, S.out, h->out_total * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1351,6 +1409,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   std::vector<Cosmo> cs(B);
   CU(cudaMemcpyAsync(cs.data(), S.cosmo, B * sizeof(Cosmo), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (sharded && h->xch->check(&xerr) != 0) return fail(RTRG_ECUDA, "k-shard exchange: %s", xerr.c_str());
   prof_collect(h);
   int worst = RTRG_OK;
   for (int b = 0; b < B; b++) {
@@ -1401,6 +1460,14 @@ int rtrg_counters(const rtrg_handle *h, int i, long long counters[4]) {
   for (int j = 0; j < 4; j++) counters[j] = h->counters[4 * i + j];
   return RTRG_OK;
 }
+int rtrg_rmax_history(rtrg_handle *h, int i, double *out, int cap) {
+  if (!h || !out || !h->prepared || i < 0 || i >= h->S.B || (size_t)(4 * i + 3) >= h->counters.size())
+    return fail(RTRG_EINVAL, "bad argument");
+  const int n = (int)std::min<long long>(std::min<long long>(h->counters[4 * i], RMAX_HIST), cap);
+  if (n > 0)
+    CU(cudaMemcpy(out, h->S.rmax_hist + (size_t)i * RMAX_HIST, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return n;
+}
 long long rtrg_launch_count(const rtrg_handle *h) { return h ? h->launches : 0; }
 long long rtrg_matvec_sets(const rtrg_handle *h, int i) {
   if (!h || i < 0 || (size_t)i >= h->matvecs.size()) return -1;
@@ -1418,7 +1485,7 @@ int rtrg_kshard_init_nccl(rtrg_handle *h, const char id[128]) {
   if (h->cfg.k_shards < 2) return fail(RTRG_EINVAL, "handle was created with k_shards = %d", h->cfg.k_shards);
   CU(cudaSetDevice(h->cfg.device));
   std::string err;
-  h->xch = make_nccl_exchange(id, h->cfg.k_shards, h->cfg.k_rank, &err);
+  h->xch = make_nccl_exchange(id, h->cfg.k_shards, h->cfg.k_rank, h->cfg.device, &err);
   if (!h->xch) return fail(RTRG_ECUDA, "%s", err.c_str());
   return RTRG_OK;
 }
@@ -1494,6 +1561,11 @@ static int scratch(rtrg_handle *h, size_t n) {
   double *p = nullptr;
   int rc = dev_alloc(h->batch_allocs, &p, n);
   if (rc) return rc;
+  if (h->d_scratch) {  // the buffer it replaces
+    auto it = std::find(h->batch_allocs.begin(), h->batch_allocs.end(), (void *)h->d_scratch);
+    if (it != h->batch_allocs.end()) h->batch_allocs.erase(it);
+    cudaFree(h->d_scratch);
+  }
   h->d_scratch = p;
   h->scratch_len = n;
   return RTRG_OK;

@@ -88,14 +88,18 @@ __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
   for (int c = 0; c < 3; c++) {
     const double *f = yb + c * tb.nk + n0;
     double lnP = tail;
+    RT_ASSERT((w0 == 0.0 || (n0 >= 0 && n0 < tb.nk)) && (w3 == 0.0 || (n0 + 3 >= 0 && n0 + 3 < tb.nk)));
+    RT_ASSERT((w1 == 0.0 || (n0 + 1 >= 0 && n0 + 1 < tb.nk)) && (w2 == 0.0 || (n0 + 2 >= 0 && n0 + 2 < tb.nk)));
     if (w0 != 0.0) lnP += w0 * f[0];
     if (w1 != 0.0) lnP += w1 * f[1];
     if (w2 != 0.0) lnP += w2 * f[2];
     if (w3 != 0.0) lnP += w3 * f[3];
     const double P = (win > 0.0) ? exp(lnP) * win : 0.0;
     P3[((long long)b * 3 + c) * tb.np + ip] = P;
-    if (ip >= tb.jlo)
+    if (ip >= tb.jlo) {
+      RT_ASSERT((BIL_R - 1) + (tb.np - 1 - ip) < tb.LP);
       Prev[((long long)b * 3 + c) * tb.LP + (BIL_R - 1) + (tb.np - 1 - ip)] = P * k2;
+    }
   }
 }
 
@@ -224,6 +228,12 @@ __global__ void __launch_bounds__(TPB, MINB)
   const double *s_c[NS];
 #pragma unroll
   for (int q = 0; q < NS; q++) s_c[q] = s_a + (q * 3 + cd_q[q]) * LP;
+  // debug build: the T window of this thread, the shared-memory windows and the slots stay inside
+  RT_ASSERT(n >= 0 && n < N_JKERN && i0 + tu < ldT && i0 / 2 + tb.NVp / 2 <= tb.NUp / 2);
+  RT_ASSERT(((size_t)n * (tb.NUp / 2) + i0 / 2 + tb.NVp / 2 - 1) * ldT + i0 + tu < (size_t)tb.n_Tc / 2);
+  RT_ASSERT(tb.NVp + R <= LP && (R - 1) + tu < LP);
+#pragma unroll
+  for (int q = 0; q < NS; q++) RT_ASSERT(e_q[q] >= 0 && cd_q[q] >= 0 && cd_q[q] < 3);
 
   double acc[R][NS];
 #pragma unroll
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (s_wrb[wv][1] == rbx) s += s_red[(wv * 2 + 1) * (NSL * R) + x];
     }
     const int part = vs * tb.nchunk + (c - (rbx * tb.NV) / TPB);
+    RT_ASSERT(part >= 0 && part < nch && c - (rbx * tb.NV) / TPB < tb.nchunk && rbx * R + r < tb.nk);
     double *dst = Jpart + (((long long)e * N_JKERN + n) * nch + part) * 9 * tb.nk + rbx * R + r;
     if (L.replicate) {
 #pragma unroll
@@ -364,6 +375,12 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------- k_pz
 // PZb[e][n][ab][i] = dlnk/(2 pi^2) k_i^3 P00(k_i) sum_m P_ab(q_m) G_n[i_pad - m]
+// One warp per output row: the lanes stride over the samples m (coalesced reads of the reversed
+// kernel row, conflict-free shared-memory reads of the spectrum) and the 32 partial sums are
+// added by a butterfly -- a chain of (np - jlo)/32 FMAs instead of np - jlo per row, which is what
+// a single cosmology (k-sharded ranks: a few dozen rows) waits for.  The order of the additions
+// does not depend on the batch or on the k-sharding.
+enum { PZ_ROWS = 16 };  // rows per CTA (4 warps x 4 rows)
 __global__ void __launch_bounds__(128)
     k_pz(IntegralTabs tb, double pre, const double *__restrict__ P3, double *__restrict__ PZb,
          int row0, int nrows, const int *__restrict__ mask, unsigned int need) {
@@ -376,13 +393,19 @@ __global__ void __launch_bounds__(128)
   for (int m = threadIdx.x; m < tb.np; m += blockDim.x) s_p[m] = Pab[m];
   __syncthreads();
   const double *G = tb.G + (long long)n * (2 * tb.np - 1) + (tb.np - 1);
-  for (int ii = threadIdx.x; ii < nrows; ii += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_end = min(nrows, (int)(blockIdx.z + 1) * PZ_ROWS);
+  for (int ii = blockIdx.z * PZ_ROWS + warp; ii < r_end; ii += 4) {
     const int i = row0 + ii, ipad = tb.nshift + i;
     double acc = 0.0;
-    for (int m = tb.jlo; m < tb.np; m++) acc = fma(s_p[m], __ldg(G + ipad - m), acc);
-    const double k = tb.kpad[ipad];
-    PZb[(((long long)e * N_ZKERN + n) * 3 + ab) * tb.nk + i] =
-        pre * (k * k * k) * P3[(long long)e * 3 * tb.np + ipad] * acc;
+    RT_ASSERT(ipad - tb.jlo <= tb.np - 1 && ipad - (tb.np - 1) >= -(tb.np - 1) && i < tb.nk);
+    for (int m = tb.jlo + lane; m < tb.np; m += 32) acc = fma(s_p[m], __ldg(G + ipad - m), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const double k = tb.kpad[ipad];
+      PZb[(((long long)e * N_ZKERN + n) * 3 + ab) * tb.nk + i] =
+          pre * (k * k * k) * P3[(long long)e * 3 * tb.np + ipad] * acc;
+    }
   }
 }
 
@@ -395,7 +418,11 @@ __device__ __forceinline__ double kpow_i(double k, double kinv, int p) {
     for (int i = 0; i < -p; i++) r *= kinv;
   return r;
 }
-enum { ASM_ROWS = 16, ASM_NV = 190 };
+// ASM_ROWS rows per CTA: 16 for batches (the term table is read once per 16 rows), 4 when the
+// launch is small (one cosmology, k-sharded ranks), where more CTAs shorten the critical path.  The
+// arithmetic per row is the same.
+enum { ASM_NV = 190 };
+template <int ASM_ROWS>
 __global__ void __launch_bounds__(256)
     k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
                const double *__restrict__ PZb, const double *__restrict__ P3,
@@ -421,6 +448,7 @@ __global__ void __launch_bounds__(256)
         // CTA along the item axis that holds some of the block's alpha-side lags
         const int nch = tb.nchunk * tb.vsplit, rb = i / BIL_R;
         const int np_rb = (rb * tb.NV + tb.NV - 1) / tb.tpb - (rb * tb.NV) / tb.tpb + 1;
+        RT_ASSERT(np_rb >= 1 && np_rb <= tb.nchunk && n < N_JKERN && pair < 9);
         for (int vs = 0; vs < tb.vsplit; vs++)
           for (int p = 0; p < np_rb; p++)
             x += Jpart[((((long long)e * N_JKERN + n) * nch + vs * tb.nchunk + p) * 9 + pair) * tb.nk + i];
@@ -454,6 +482,7 @@ __global__ void __launch_bounds__(256)
     for (int t = tb.t_start[o]; t < t1; t++) {
       const int s = tb.t_src[t];
       const int v = (s == 3) ? 189 : s * 63 + tb.t_index[t];
+      RT_ASSERT(v >= 0 && v < ASM_NV && t < tb.n_terms);
       acc += tb.t_coef[t] * kpow_i(k, kinv, tb.t_kpow[t]) * vals[v][rr];
     }
     src[((long long)e * N_SRC + o) * tb.nk + i] = acc;
@@ -562,7 +591,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     if (groups & (1 << gi)) need_pz |= tb.need_pz[gi];
   if (groups & GRP_RAW) need_pz = (1u << (N_ZKERN * 3)) - 1u;
   if (need_pz) {
-    dim3 g(N_ZKERN * 3, B);
+    dim3 g(N_ZKERN * 3, B, (nrows + PZ_ROWS - 1) / PZ_ROWS);
     const double pre = tb.dlnk / (2.0 * M_PI * M_PI);  // rt:719
     RT_TIC(prof, PC_PZ, st);
     k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask, need_pz);
@@ -570,10 +599,13 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     launches++;
   }
   {
-    dim3 g((nrows + ASM_ROWS - 1) / ASM_ROWS, B);
     RT_TIC(prof, PC_ASSEMBLE, st);
-    k_assemble<<<g, 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
-                                  nrows, mask, groups);
+    if ((long long)B * nrows <= 2048)
+      k_assemble<4><<<dim3((nrows + 3) / 4, B), 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
+                                                             nrows, mask, groups);
+    else
+      k_assemble<16><<<dim3((nrows + 15) / 16, B), 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw,
+                                                               row0, nrows, mask, groups);
     RT_TOC(prof, st);
     launches++;
   }

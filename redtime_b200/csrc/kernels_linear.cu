@@ -51,6 +51,13 @@ __global__ void k_prep_inputs(Batch S, const double *__restrict__ T0) {
   const int b = blockIdx.y;
   const Cosmo &c = S.cosmo[b];
   const double f_b = c.Ob / (c.Om - c.On), f_c = 1.0 - f_b, t0 = T0[b];
+  // debug build: every table of this cosmology lies inside the input pool
+  RT_ASSERT(c.offT >= 0 && c.offT + c.nT <= S.n_in && c.offLT >= 0 && c.offLT + c.nT <= S.n_in && c.offTb >= 0 &&
+            c.offTb + c.nT <= S.n_in);
+  RT_ASSERT(c.n_z == 0 || (c.offA >= 0 && c.offA + c.n_z <= S.n_in && c.offKb >= 0 && c.offKb + c.n_kb <= S.n_in));
+  RT_ASSERT(c.n_z == 0 || c.offRow1 < 0 || (c.offRow1 + c.n_kb <= S.n_in && c.offBred + (long long)c.n_z * S.nkk <= S.n_in));
+  RT_ASSERT(c.n_z == 0 || c.offRow1 >= 0 || c.offB + (long long)c.n_z * c.n_kb <= S.n_in);
+  RT_ASSERT(c.offTc < 0 || c.offTc + (long long)c.n_z * c.n_kb <= S.n_in);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.nT; i += gridDim.x * blockDim.x) {
     const double Ti = f_b * S.in[c.offTb + i] + f_c * S.in[c.offLT + i];
     S.in[c.offT + i] = log(S.in[c.offT + i]);

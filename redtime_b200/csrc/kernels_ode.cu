@@ -86,6 +86,11 @@ __device__ __forceinline__ void rhs_row_coeffs(const Batch &S, const Cosmo &c, i
   }
 }
 
+// SPLIT = false: one thread per row does the four pieces of the row one after the other (batches:
+// fewest redundant coefficient evaluations).  SPLIT = true: a thread per (row, piece), 32 rows per
+// block -- a quarter of the serial work per thread, for launches too small to fill the GPU (one
+// cosmology, k-sharded ranks).  Same arithmetic per component either way.
+template <bool SPLIT>
 __global__ void __launch_bounds__(128)
     k_rhs(Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv,
           double *__restrict__ dyv, int stage, const int *__restrict__ mask) {
@@ -96,7 +101,8 @@ __global__ void __launch_bounds__(128)
   __shared__ RhsShared sh;
   if (threadIdx.x == 0) rhs_time_setup(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
   __syncthreads();
-  const int i = S.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const int piece = SPLIT ? (int)(threadIdx.x >> 5) : -1;
+  const int i = S.k_lo + (SPLIT ? blockIdx.x * 32 + (threadIdx.x & 31) : blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= S.k_hi) return;
   const double eeta = sh.eeta;
   const double k = kgrid[i];
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(128)
 
   // The row is processed in four pieces (ln P + I, then the three multipoles of Q) so that at
   // most 17 + 14 + 17 values are live at a time: 4x the occupancy of holding all 41 + 38 + 41.
-  {
+  if (!SPLIT || piece == 0) {
     double y[N_UP + N_UI], dy[N_UP + N_UI], A14[N_UI];
 #pragma unroll
     for (int j = 0; j < N_UP + N_UI; j++) y[j] = yb[(long long)j * nk];
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(128)
   }
 #pragma unroll
   for (int l = 0; l < 3; l++) {
+    if (SPLIT && piece != l + 1) continue;
     double Q[8], R[8], dQ[8];
     const int j0 = N_UP + N_UI + 8 * l;
     if (c.sw_nl && evolve_Q) {
@@ -392,6 +399,7 @@ __global__ void k_ctrl_begin(Batch S) {
   S.m_full_step[b] = S.m_full_acc[b] = S.m_out_int[b] = S.m_loc_step[b] = 0;
   if (S.done[b]) return;
   const Cosmo &c = S.cosmo[b];
+  RT_ASSERT(S.i_out[b] >= 0 && S.i_out[b] < MAX_OUT && S.i_out[b] < c.n_out);
   const double target = S.etaout[(long long)b * MAX_OUT + S.i_out[b]];
   const double t = S.t[b], h = S.h[b];
   if ((target - t) * h > 0) {  // rt:1614
@@ -435,6 +443,7 @@ __global__ void k_ctrl_end(Batch S, int max_attempts) {
   const double target = S.etaout[(long long)b * MAX_OUT + S.i_out[b]];
   const double h_old = S.h_try[b];
   const double t_new = S.final_step[b] ? target : S.t[b] + h_old;
+  if (cnt[0] < RMAX_HIST) S.rmax_hist[(long long)b * RMAX_HIST + cnt[0]] = rmax;
   cnt[0]++;
   cnt[2] += 5;
   double h0 = h_old;
@@ -484,6 +493,7 @@ __global__ void k_stash(Batch S) {
   const long long n = (long long)N_U * S.nk;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = S.vbase[b] + S.i_out[b];
+  RT_ASSERT(v >= 0 && v < S.NO && S.i_out[b] < S.cosmo[b].n_out);
   if (idx == 0) {
     S.vc_have[v] = 1;
     S.t_stash[v] = S.t[b];
@@ -610,13 +620,17 @@ __global__ void __launch_bounds__(128) k_output(Batch S, const double *__restric
   }
   if (S.print_Q)
     for (int j = 0; j < N_UQ; j++) row[col++] = y[(long long)(N_UP + N_UI + j) * nk] * a3;
+  RT_ASSERT(col == ncols && (row - S.out) + ncols <= S.n_out_total && v < S.NO && io < c.n_out);
 }
 
 // ---------------------------------------------------------------------------- launchers
 void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *dyv, int stage,
                 const int *mask, cudaStream_t st) {
   const int nrows = S.k_hi - S.k_lo;
-  k_rhs<<<dim3((nrows + 127) / 128, S.B), 128, 0, st>>>(S, kgrid, yv, dyv, stage, mask);
+  if ((long long)S.B * nrows <= 2048)
+    k_rhs<true><<<dim3((nrows + 31) / 32, S.B), 128, 0, st>>>(S, kgrid, yv, dyv, stage, mask);
+  else
+    k_rhs<false><<<dim3((nrows + 127) / 128, S.B), 128, 0, st>>>(S, kgrid, yv, dyv, stage, mask);
 }
 static size_t attempt_smem_bytes() { return (size_t)RK_STAGES * (N_UP + N_UI + 24) * ATT_ROWS * sizeof(double); }
 int ode_configure() {

@@ -23,9 +23,20 @@
 #include <vector>
 #endif
 
+// -DRTRG_BOUNDS: the debug build (libredtime_b200_bounds.so) checks every computed index against
+// the extent of the array it addresses with device-side asserts -- the stand-in for
+// compute-sanitizer's memcheck, which is closed on the GPU pool.  tests/test_gpu_bounds.py runs the
+// end-to-end paths on that build; a violated assert surfaces as cudaErrorAssert.
+#ifdef RTRG_BOUNDS
+#include <cassert>
+#define RT_ASSERT(cond) assert(cond)
+#else
+#define RT_ASSERT(cond) ((void)0)
+#endif
+
 namespace rtrg {
 
-enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55 };
+enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55, RMAX_HIST = 128 };
 #ifndef RTRG_NKERN_DEFINED
 #define RTRG_NKERN_DEFINED
 enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
@@ -44,6 +55,7 @@ struct IntegralTabs {
   int ldT;     // leading dimension of the compact kernel table
   int nchunk;  // partial sums per row block: the most CTAs along the item axis one row block spans
   int tpb;     // threads per CTA of the bilinear kernel
+  long long n_Tc;  // doubles in Tc (bounds checks of the debug build)
   int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
@@ -73,6 +85,7 @@ struct Batch {
   double eps_abs, eps_rel, z1l, beta_kmin, beta_kmax, a_early;
   int print_A, print_I, print_Q, print_bias;
   int k_lo, k_hi;  // k-rows owned by this rank (k-sharding); [0,nk) otherwise
+  long long n_in, n_out_total, n_slots;  // extents of in, out and of the integral work space (in cosmologies)
   Cosmo *cosmo;            // [B]
   double *zout, *aout, *etaout;  // [B][MAX_OUT] output redshifts, 1/(1+z), ln(a/a_in)
   // pooled input tables (one buffer; per-cosmology offsets in Cosmo)
@@ -100,6 +113,7 @@ struct Batch {
   int *m_loc_step;  // stepping cosmologies whose RHS needs no new integrals (k_attempt_local)
   void *att_time;   // [B][RK_STAGES] time-only stage quantities of the current attempt (k_attempt_setup)
   long long *counters;     // [B][4]
+  double *rmax_hist;       // [B][RMAX_HIST] error norm of every attempt (diagnostics: decision margins)
   long long *matvecs;      // [B] (kernel, spectrum) matrix-vector sets executed since device_init
   int *act, *nact;         // [B], [1] compacted list of the cosmologies of the current launch
   int *n_active;           // [1]

@@ -156,3 +156,18 @@ def write_run_dir(path, c):
     assert np.array_equal(c["Tc_T"], c["Tc_b"][-1])
     _write_camb(os.path.join(path, "camb_transfer_z0.dat"), c["k_T"], c["Tc_T"], c["Tb_T"], c["Tnu_b"][-1])
     return path
+
+
+def perturbed_run_dir(src, dst, line=1, direction=+1):
+    """Copy run directory src to dst with ONE value of params_redTime.dat moved by one ulp (line 0 =
+    n_s, 1 = sigma_8, ...).  Running the reference on both measures its own round-off floor: how far
+    its tables move under a change of the input that is 1e-10 below every tolerance."""
+    import shutil
+    shutil.copytree(src, dst)
+    p = os.path.join(dst, "params_redTime.dat")
+    txt = open(p).read().split("\n")
+    vals = [n for n, l in enumerate(txt) if l.strip() and not l.startswith("#")]
+    x = float(txt[vals[line]].split()[0])
+    txt[vals[line]] = "%.17g" % np.nextafter(x, np.inf if direction > 0 else -np.inf)
+    open(p, "w").write("\n".join(txt))
+    return dst

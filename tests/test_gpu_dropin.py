@@ -81,11 +81,26 @@ def test_table_cache_round_trip(tmp_path, example1_dir, stage_golden_1loop, monk
         res.append(h.integrals_raw(g["yp"][:3 * 128]))
         h.close()
     files = os.listdir(str(tmp_path / "cache"))
-    assert len(files) == 1 and files[0].startswith("T_v2_nk128_")
+    assert len(files) == 1 and files[0].startswith("T_v3_nk128_")
     for a, b in zip(res[0][:3], res[1][:3]):
         assert np.array_equal(a, b)
     assert res[0][3] == res[1][3]
     assert dt[1] < dt[0]
+    # a damaged file (one flipped byte anywhere in the 24 MB) must be detected -- the checksum covers
+    # every byte -- and rebuilt, not trusted
+    path = os.path.join(str(tmp_path / "cache"), files[0])
+    good = open(path, "rb").read()
+    bad = bytearray(good)
+    bad[len(bad) // 2 + 12345] ^= 0x10
+    open(path, "wb").write(bytes(bad))
+    h = rt.RedTimeB200()
+    h.add_cosmology(rt.read_run_dir(example1_dir))
+    h.prepare()
+    again = h.integrals_raw(g["yp"][:3 * 128])
+    h.close()
+    for a, b in zip(res[0][:3], again[:3]):
+        assert np.array_equal(a, b)
+    assert open(path, "rb").read() == good      # rewritten from the rebuilt tables
     monkeypatch.setenv("RTRG_CACHE_DIR", "off")
     h = rt.RedTimeB200()
     h.close()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import redtime_b200 as rt
-from conftest import GOLDEN, parse_tables, load_floor, assert_table_parity
+from conftest import GOLDEN, parse_tables, load_floor, assert_table_parity, gpu_table_with_floor, local_scale
 
 pytestmark = pytest.mark.gpu
 
@@ -17,15 +17,11 @@ def test_high_accuracy_build_of_the_reference(example1_dir):
     with gzip.open(os.path.join(GOLDEN, "example1_oracle_HIGH_ACCURACY_1loop.dat.gz"), "rt") as f:
         hdr, ref = parse_tables(f.read())
     ref = ref.reshape(7, 512, 17)
-    h = rt.RedTimeB200(nk=512, eps_abs=1e-15, eps_rel=1e-6)
-    h.add_cosmology(rt.read_run_dir(example1_dir))
-    h.prepare()
-    tables, hd, hd0, status = h.run()
-    cnt = h.counters(0)
-    h.close()
-    assert not status.any()
-    tab = tables[0]
+    tab, own, cnt = gpu_table_with_floor(example1_dir, nk=512, eps_abs=1e-15, eps_rel=1e-6)
     assert tab.shape == ref.shape
     assert cnt["attempts"] > 100          # the tight tolerance takes hundreds of steps
-    # every k and column; the floor is larger at np = 2048 and was measured with this oracle build
-    assert_table_parity(tab, ref, load_floor("HIGH_ACCURACY_1loop"), what="HIGH_ACCURACY")
+    # every k and column: tolerance + 5 x (the oracle's floor at np = 2048 + this library's own; here the
+    # dense quadrature is the noisier side: 1.5e-4 relative in columns 15-17 below k = 4e-3 h/Mpc against
+    # the reference's 5e-6 -- sums of 1.7 M products against FFTs, tools/diag_floor.py)
+    assert_table_parity(tab, ref, load_floor("HIGH_ACCURACY_1loop") + own, what="HIGH_ACCURACY")
+    assert np.max(own[:, :, 10:] / (local_scale(ref)[:, :, 10:] + 1e-300)) < 2e-3

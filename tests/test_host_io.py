@@ -125,3 +125,71 @@ def test_camb_modern_13_column_files(tmp_path):
     # read as 7-column files the rows no longer line up: the k lists of the files disagree
     with pytest.raises(rt.RtrgError):
         rt.read_run_dir(d, camb_modern=False)
+
+
+def test_fast_parser_equals_numpy_on_ragged_files(tmp_path):
+    """The table reader converts only the columns the run consumes, takes an exact fast path for
+    short decimal mantissas and a fixed-width shortcut once a row's layout is known.  Files that
+    break every one of those assumptions must still give the doubles np.loadtxt (strtod) gives:
+    rows of changing width, 17-digit mantissas, explicit '+' signs, huge/tiny exponents, comment
+    lines between the rows of the z = 0 file, CRLF line ends."""
+    rng = np.random.default_rng(11)
+    n = 257
+    d = str(tmp_path / "r")
+    os.makedirs(d)
+    k = np.sort(np.exp(rng.uniform(np.log(1e-5), np.log(50.0), n)))
+    zs = ["10", "1", "0"]
+
+    def fmt(x, i, j):
+        style = (i + j) % 5
+        if i < 40:
+            return "%14.6E" % x                       # CAMB's fixed-width block first: the layout is learnt ...
+        if style == 0:
+            return "%.17e" % x                        # ... and then broken in every way
+        if style == 1:
+            return "+%.9g" % x
+        if style == 2:
+            return "   %.5E" % x
+        if style == 3:
+            return "%.12f" % x
+        return "%25.16e" % x
+
+    tabs = {}
+    for z in zs:
+        cols = np.abs(rng.standard_normal((n, 7))) * 10.0 ** rng.integers(-30, 30, size=(n, 7))
+        cols[:, 0] = k
+        lines = [" ".join(fmt(cols[i, j], i, j) for j in range(7)) for i in range(n)]
+        txt = ("\r\n" if z == "1" else "\n").join(lines) + "\n"
+        open(os.path.join(d, "camb_transfer_z%s.dat" % z), "w").write(txt)
+        tabs[z] = np.loadtxt(os.path.join(d, "camb_transfer_z%s.dat" % z))
+        if z == "0":   # the z = 0 transfer file proper may carry comments between its rows (hdr:805-821)
+            for i in range(n - 1, 0, -50):
+                lines.insert(i, "# a comment between rows")
+            open(os.path.join(d, "transfer_main.dat"), "w").write("\n".join(lines) + "\n")
+    p = ["# ragged", "0.96", "0.8", "0.7", "0.3", "0.045", "0.004", "2.726", "-1", "0", "1", "1", "1", "1", "200", "2",
+         "1 0", "transfer_main.dat", "0", "camb_transfer_z", "3", " ".join(zs)]
+    open(os.path.join(d, "params_redTime.dat"), "w").write("\n".join(p) + "\n")
+    c = rt.read_run_dir(d)
+    assert np.array_equal(c["k_T"], tabs["0"][:, 0]) and np.array_equal(c["Tc_T"], tabs["0"][:, 1])
+    assert np.array_equal(c["Tb_T"], tabs["0"][:, 2])
+    for iz, z in enumerate(zs):
+        assert np.array_equal(c["Tc_b"][iz], tabs[z][:, 1]) and np.array_equal(c["Tnu_b"][iz], tabs[z][:, 5]), z
+    assert np.array_equal(c["k_b"], tabs["10"][:, 0])
+
+
+def test_number_format_is_printf_20_12g():
+    """The table printer formats with std::to_chars(general, 12) instead of printf: every value must
+    come out exactly as "%20.12g" (what setw(20) << setprecision(12) prints, rt:1670-1737)."""
+    import ctypes as C
+    lib = rt.load_library()
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.standard_normal(20000) * 10.0 ** rng.integers(-320, 300, 20000),
+                        [0.0, -0.0, 1.0, 1e-5, 9.99999999999949e-5, 9.999999999995e-5, 123456789012.0, 999999999999.5,
+                         1e12, 1e11, 0.1, 1e-4, 1e-300, 5e-324, 1.7976931348623157e308, 100000.0, 1e21, 0.001,
+                         np.inf, -np.inf]])
+    buf = C.create_string_buffer(20 * v.size + 1)
+    lib.rtrg_format_g12.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_char_p]
+    assert lib.rtrg_format_g12(v.ctypes.data_as(C.POINTER(C.c_double)), int(v.size), buf) == 0
+    got = buf.value.decode()
+    for i, x in enumerate(v):
+        assert got[20 * i:20 * i + 20] == "%20.12g" % x, (x, got[20 * i:20 * i + 20], "%20.12g" % x)

@@ -29,7 +29,7 @@ for rb in (1, 0):
     h.add_cosmologies(cosmos)
     h.prepare()
     tables, hdr, hdr0, status = h.run()
-    res[rb] = (tables, [h.counters(i) for i in range(N)], status.copy())
+    res[rb] = (tables, [h.counters(i) for i in range(N)], status.copy(), [h.rmax_history(i) for i in range(N)])
     h.close()
 refs = [parse_tables(p.communicate()[0].decode())[1].reshape(8, 128, 17) for p in procs]
 np.set_printoptions(linewidth=220, precision=2)
@@ -47,6 +47,14 @@ for i in range(N):
     p = cosmos[i]["params"]
     line += "  w0 %.3f wa %.3f On %.5f h %.3f" % (p[7], p[8], p[5], p[2])
     print(line)
+    r1, r0 = res[1][3][i], res[0][3][i]
+    m = np.minimum(np.abs(r1 / 1.1 - 1), np.abs(r1 / 0.5 - 1))
+    j = int(np.argmin(m))
+    print("      attempt with the smallest decision margin: #%d rmax = %.15g (margin %.2e); rmax rb=1 vs rb=0 max rel diff "
+          "over the common prefix %.2e" % (j, r1[j], m[j], np.max(np.abs(r1[:min(len(r1), len(r0))] / r0[:min(len(r1), len(r0))] - 1))))
+    if len(r1) != len(r0) or i == 15:
+        print("      rmax rb=1:", np.array2string(r1, precision=6))
+        print("      rmax rb=0:", np.array2string(r0, precision=6))
     out["gpu%d" % i], out["ref%d" % i] = res[1][0][i], r
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.savez_compressed(os.path.join(ROOT, "gpurun_out", "diag_parity.npz"), **out)
