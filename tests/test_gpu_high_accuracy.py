@@ -24,4 +24,6 @@ def test_high_accuracy_build_of_the_reference(example1_dir):
     # dense quadrature is the noisier side: 1.5e-4 relative in columns 15-17 below k = 4e-3 h/Mpc against
     # the reference's 5e-6 -- sums of 1.7 M products against FFTs, tools/diag_floor.py)
     assert_table_parity(tab, ref, load_floor("HIGH_ACCURACY_1loop") + own, what="HIGH_ACCURACY")
-    assert np.max(own[:, :, 10:] / (local_scale(ref)[:, :, 10:] + 1e-300)) < 2e-3
+    from conftest import smooth_floor
+    assert np.all(smooth_floor(own)[:, :, 10:] <= 60 * smooth_floor(load_floor("HIGH_ACCURACY_1loop"))[:, :, 10:] +
+                  1e-5 * local_scale(ref)[:, :, 10:])    # measured: median 16 x in columns 16-17 below k = 4e-3
