@@ -26,7 +26,7 @@ namespace rtrg {
 // kernels_integrals.cu
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int groups, int identical,
-                     cudaStream_t st, Profiler *prof);
+                     cudaStream_t st, Profiler *prof, const SideStream *side = nullptr);
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st);
 int integrals_configure(const IntegralTabs &tb);
@@ -149,6 +149,7 @@ struct rtrg_handle {
   bool d_in_transformed = false;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_done = nullptr;
+  SideStream side;  // parallel launch branch of the integral evaluations
   // pinned host mirror of the outputs (rtrg_fetch_outputs)
   double *h_out = nullptr;
   size_t h_out_cap = 0;
@@ -380,6 +381,9 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       rtrg_destroy(h);
       return fail(RTRG_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
@@ -518,6 +522,10 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   }
   for (int r = 0; r < N_SRC; r++) t_start[r + 1] += t_start[r];
   tb.n_terms = (int)terms.size();
+  if (tb.n_terms > 768) {  // k_assemble keeps the table in shared memory (ASM_MAXT)
+    rtrg_destroy(h);
+    return fail(RTRG_EINVAL, "assembly table has %d terms, the kernel holds 768", tb.n_terms);
+  }
   // which (kernel, beta-side spectrum) products each output group consumes
   std::memset(tb.need_cd, 0, sizeof tb.need_cd);
   std::memset(tb.need_pz, 0, sizeof tb.need_pz);
@@ -569,6 +577,9 @@ int rtrg_destroy(rtrg_handle *h) {
   h->stage.release();
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
+  if (h->side.fork) cudaEventDestroy(h->side.fork);
+  if (h->side.join) cudaEventDestroy(h->side.join);
+  if (h->side.stream) cudaStreamDestroy(h->side.stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -1235,7 +1246,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     std::vector<int> m(B);
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof);
+    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof, &h->side);
     ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, h->d_minit, st));
   }
 
@@ -1262,7 +1273,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
       for (int s = 1; s < RK_STAGES; s++) {
         ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.m_full_step, st));
         XCH(gather_lnP(S.ytmp));
-        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, grp_rhs(h), 0, st, h->prof);
+        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, grp_rhs(h), 0, st, h->prof, &h->side);
         ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.ytmp, S.kst + (size_t)s * NE, s, S.m_full_step, st));
       }
       ODE_LAUNCH(PC_FINAL, launch_final(S, S.m_full_step, st));
@@ -1272,7 +1283,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
     XCH(gather_lnP(S.y));  // keep ln P of the accepted state complete on every rank
     if (h->any_full) {  // dydt_in of the next attempt
-      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof);
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof, &h->side);
       ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.m_full_acc, st));
     }
     return RTRG_OK;
@@ -1390,7 +1401,7 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
       SV.cosmo = S.cosmo_v + v0;
       SV.matvecs = S.matvecs_v + v0;
       h->launches += launch_integrals(tb, SV, S.ystash + (size_t)v0 * N_U * nk, (long long)N_U * nk, S.src_v, nullptr,
-                                      S.vc_mask + v0, grp_out(h), 0, st, h->prof);
+                                      S.vc_mask + v0, grp_out(h), 0, st, h->prof, &h->side);
     }
     ODE_LAUNCH(PC_OUTPUT, launch_output(S, h->d_kgrid, v0, nv, st));
   }

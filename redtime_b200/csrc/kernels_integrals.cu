@@ -3,7 +3,7 @@
 //
 //   k_extrap           Pab extrapolation + window (rt:181-232, 772-778)        HBM/latency bound
 //   k_bilinear(_packed) J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]   FP64 FMA pipe bound
-//   k_compact          list of the cosmologies a launch is masked in for
+//   (compact_mask)     list of the cosmologies a launch is masked in for, built inside k_extrap
 //   k_jlo              J_0 at the low-k row nloMR (rt:1252,1267-1272)
 //   k_pz               P13-type log-convolutions PZ_n (rt:689-727)
 //   k_assemble         A_{acd,bef}, R^l_{abc}, P_T,jm, P_MR,n from the table of assembly_table.cc
@@ -68,11 +68,28 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // ---------------------------------------------------------------------------- k_extrap
+// act[0..*nact) = the unmasked cosmologies of a launch in ascending order: the slot list of
+// k_bilinear.  One warp (ballot + popc prefix); done by the first warp of k_extrap's first block,
+// which saves a launch per evaluation.
+__device__ __forceinline__ void compact_mask(const int *__restrict__ mask, int B, int *__restrict__ act,
+                                             int *__restrict__ nact, int lane) {
+  int off = 0;
+  for (int base = 0; base < B; base += 32) {
+    const int b = base + lane;
+    const int m = (b < B) && (!mask || mask[b]);
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (m) act[off + __popc(bal & ((1u << lane) - 1u))] = b;
+    off += __popc(bal);
+  }
+  if (lane == 0) *nact = off;
+}
 // y: state vectors [B][ystride]; only the three ln P components are read.
 __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
                          const double *__restrict__ y, long long ystride,
                          double *__restrict__ P3, double *__restrict__ Prev,
-                         const int *__restrict__ mask, long long *__restrict__ matvecs, int units) {
+                         const int *__restrict__ mask, long long *__restrict__ matvecs, int units,
+                         int *__restrict__ act, int *__restrict__ nact) {
+  if (act && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32) compact_mask(mask, gridDim.y, act, nact, threadIdx.x);
   const int b = blockIdx.y;
   if (mask && !mask[b]) return;
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,20 +164,7 @@ struct BilLaunch {
 // same T stream, taken from consecutive entries of the list {active cosmologies} x {spectra of
 // the item}, so every T element feeds 8 rows x 3 slots = 24 DFMAs whatever the number of spectra
 // the item needs (1 for the 1-loop cache, 2 for most P_T,jm kernels, 3 inside the RHS).
-// act[0..*nact) lists the unmasked cosmologies in ascending order (k_compact).
-__global__ void k_compact(const int *__restrict__ mask, int B, int *__restrict__ act, int *__restrict__ nact) {
-  const int lane = threadIdx.x;
-  int off = 0;
-  for (int base = 0; base < B; base += 32) {
-    const int b = base + lane;
-    const int m = (b < B) && (!mask || mask[b]);
-    const unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (m) act[off + __popc(bal & ((1u << lane) - 1u))] = b;
-    off += __popc(bal);
-  }
-  if (lane == 0) *nact = off;
-}
-
+// act[0..*nact) lists the unmasked cosmologies in ascending order (compact_mask in k_extrap).
 // R: output rows per row block; TPB: threads; VC: beta-side lags per software-pipelined chunk.
 //
 // Work distribution.  A row block (R consecutive output rows) needs one thread per alpha-side lag,
@@ -421,7 +425,7 @@ __device__ __forceinline__ double kpow_i(double k, double kinv, int p) {
 // ASM_ROWS rows per CTA: 16 for batches (the term table is read once per 16 rows), 4 when the
 // launch is small (one cosmology, k-sharded ranks), where more CTAs shorten the critical path.  The
 // arithmetic per row is the same.
-enum { ASM_NV = 190 };
+enum { ASM_NV = 190, ASM_MAXT = 768 };
 template <int ASM_ROWS>
 __global__ void __launch_bounds__(256)
     k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
@@ -431,6 +435,18 @@ __global__ void __launch_bounds__(256)
   const int e = blockIdx.y;
   if (mask && !mask[e]) return;
   __shared__ double vals[ASM_NV][ASM_ROWS + 1];
+  // the assembly table (730 terms, 10 KB) once per CTA: the term loops then run out of shared memory
+  // instead of chains of dependent global loads
+  __shared__ double s_coef[ASM_MAXT];
+  __shared__ short s_src[ASM_MAXT], s_index[ASM_MAXT], s_kpow[ASM_MAXT];
+  __shared__ int s_start[N_SRC + 1];
+  for (int t = threadIdx.x; t < tb.n_terms; t += blockDim.x) {
+    s_coef[t] = tb.t_coef[t];
+    s_src[t] = tb.t_src[t];
+    s_index[t] = tb.t_index[t];
+    s_kpow[t] = tb.t_kpow[t];
+  }
+  for (int t = threadIdx.x; t <= N_SRC; t += blockDim.x) s_start[t] = tb.t_start[t];
   const int r0 = row0 + blockIdx.x * ASM_ROWS;
   const int rows = min(ASM_ROWS, row0 + nrows - r0);
   const int has_jn0 = cosmo[e].sw_pr;
@@ -478,12 +494,12 @@ __global__ void __launch_bounds__(256)
     const int i = r0 + rr;
     const double k = tb.kgrid[i], kinv = 1.0 / k;
     double acc = 0.0;
-    const int t1 = tb.t_start[o + 1];
-    for (int t = tb.t_start[o]; t < t1; t++) {
-      const int s = tb.t_src[t];
-      const int v = (s == 3) ? 189 : s * 63 + tb.t_index[t];
+    const int t1 = s_start[o + 1];
+    for (int t = s_start[o]; t < t1; t++) {
+      const int s = s_src[t];
+      const int v = (s == 3) ? 189 : s * 63 + s_index[t];
       RT_ASSERT(v >= 0 && v < ASM_NV && t < tb.n_terms);
-      acc += tb.t_coef[t] * kpow_i(k, kinv, tb.t_kpow[t]) * vals[v][rr];
+      acc += s_coef[t] * kpow_i(k, kinv, s_kpow[t]) * vals[v][rr];
     }
     src[((long long)e * N_SRC + o) * tb.nk + i] = acc;
   }
@@ -528,9 +544,14 @@ static auto bil_dispatch(F &&f) {
 // Evaluation for every (unmasked) cosmology: y -> the source rows of the requested output
 // groups (GRP_* bits; GRP_ALL also fills raw J/PZ/Jn0 when raw != nullptr).  identical != 0:
 // the three spectra in y are the same array (1-loop cache).  Returns the number of launches.
+// side: optional second stream + fork/join events.  The P13-type convolutions (k_pz) and k_jlo only
+// need the extrapolated spectra, not the bilinear sums, so they run beside k_bilinear (a parallel
+// branch of the captured graph) and k_assemble joins the two: off the critical path of a single
+// cosmology, where every kernel of an evaluation is latency bound.  Not used while per-kernel
+// event timing is on.
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int groups, int identical,
-                     cudaStream_t st, Profiler *prof) {
+                     cudaStream_t st, Profiler *prof, const SideStream *side) {
   const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
   int launches = 0;
   // work items: kernel n with the beta-side spectra the requested groups consume
@@ -556,13 +577,17 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
   {
     dim3 g((tb.np + 127) / 128, B);
     RT_TIC(prof, PC_EXTRAP, st);
-    k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, S.matvecs, units);
+    k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, S.matvecs, units, S.act, S.nact);
     RT_TOC(prof, st);
     launches++;
   }
+  const bool fork = side && side->stream && !prof;
+  cudaStream_t st_side = fork ? side->stream : st;
+  if (fork) {
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(st_side, side->fork, 0);
+  }
   RT_TIC(prof, PC_BILINEAR, st);
-  k_compact<<<1, 32, 0, st>>>(mask, B, S.act, S.nact);
-  launches++;
   if (nitems) {
     // z covers the slot triples of the widest item of this launch; CTAs beyond an item's own
     // slot count exit at once
@@ -581,7 +606,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
   RT_TOC(prof, st);
   if (groups & GRP_PMR) {
     RT_TIC(prof, PC_JLO, st);
-    k_jlo<<<B, 256, tb.nsup * sizeof(double), st>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
+    k_jlo<<<B, 256, tb.nsup * sizeof(double), st_side>>>(tb, tb.kfac_lo, S.Prev, S.Jlo, mask);
     RT_TOC(prof, st);
     launches++;
   }
@@ -594,9 +619,13 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     dim3 g(N_ZKERN * 3, B, (nrows + PZ_ROWS - 1) / PZ_ROWS);
     const double pre = tb.dlnk / (2.0 * M_PI * M_PI);  // rt:719
     RT_TIC(prof, PC_PZ, st);
-    k_pz<<<g, 128, tb.np * sizeof(double), st>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask, need_pz);
+    k_pz<<<g, 128, tb.np * sizeof(double), st_side>>>(tb, pre, S.P3, S.PZb, row0, nrows, mask, need_pz);
     RT_TOC(prof, st);
     launches++;
+  }
+  if (fork) {
+    cudaEventRecord(side->join, st_side);
+    cudaStreamWaitEvent(st, side->join, 0);
   }
   {
     RT_TIC(prof, PC_ASSEMBLE, st);
@@ -615,7 +644,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st) {
   dim3 g((tb.np + 127) / 128, S.B);
-  k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, nullptr, 0);
+  k_extrap<<<g, 128, 0, st>>>(tb, S.cosmo, y, ystride, S.P3, S.Prev, mask, nullptr, 0, nullptr, nullptr);
 }
 
 int integrals_configure(const IntegralTabs &tb) {

@@ -61,6 +61,46 @@ __device__ __forceinline__ void rhs_time_setup(const Batch &S, const Cosmo &c, d
   if (sh.growth_ok) sh.xg = tab_row_x_prepare(S.lna, S.n_lna + 1, log(sh.a));
   sh.pre4 = exp(-4.0 * eta);
 }
+// The same, by all threads of a block together (k_rhs): the two table look-ups of rhs_time_setup are
+// binary searches -- chains of 4 + 7 dependent global loads, ~7 us of pure latency in front of every
+// right-hand side of a single cosmology.  Here every thread compares ONE node with the abscissa and
+// __syncthreads_count adds the votes: tab_find(x, n, xq) = #{1 <= i <= n-2 : x[i] < xq} for a sorted
+// table, one memory round trip.  Same index, same weights, same bits.
+__device__ __forceinline__ void rhs_time_setup_block(const Batch &S, const Cosmo &c, double eta, RhsShared &sh) {
+  const double A = c.a_in * exp(eta);
+  const bool beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10), beta_bad = (!beta_zero && A > 1.001);
+  const bool need_b = !beta_zero && !beta_bad;
+  const double xb = A > 1.0 ? 1.0 : A;
+  const double z = exp(-eta) * (1.0 + c.z_in) - 1, a = 1.0 / (z + 1.0);
+  const bool growth_ok = !(a > GROWTH_A_MAX || a < GROWTH_A_MIN);
+  const double xg = log(a);
+  const int nA = c.n_z, nG = S.n_lna + 1, nmax = nA > nG ? nA : nG;
+  const double *xa = S.in + c.offA;
+  int nb = 0, ng = 0;
+  for (int base = 0; base < nmax; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    nb += __syncthreads_count(need_b && i >= 1 && i <= nA - 2 && xa[i] < xb);
+    ng += __syncthreads_count(growth_ok && i >= 1 && i <= nG - 2 && S.lna[i] < xg);
+  }
+  if (threadIdx.x == 0) {
+    sh.eta = eta;
+    sh.eeta = exp(eta);
+    sh.A = A;
+    sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
+    sh.Om11 = 3.0 + bg_dlnH(c, A);
+    sh.beta_zero = beta_zero;
+    sh.beta_bad = beta_bad;
+    if (need_b) sh.xb = tab_row_x_prepare_at(xa, nA, xb, nb);
+    sh.pre4 = exp(-4.0 * eta);
+  }
+  if (threadIdx.x == 32 % blockDim.x) {
+    sh.z = z;
+    sh.a = a;
+    sh.growth_ok = growth_ok;
+    if (growth_ok) sh.xg = tab_row_x_prepare_at(S.lna, nG, xg, ng);
+  }
+  __syncthreads();
+}
 // row-dependent coefficients of that evaluation: Omega_10, and in 1-loop mode the rescaling of the
 // z1l cache, sources x (D/D_z1l)^4 e^{-4 eta} f^n (rt:1316-1337): *pre and f = *fz
 __device__ __forceinline__ void rhs_row_coeffs(const Batch &S, const Cosmo &c, int b, int i, const RhsShared &sh,
@@ -99,8 +139,7 @@ __global__ void __launch_bounds__(128)
   const Cosmo &c = S.cosmo[b];
   const int nk = S.nk;
   __shared__ RhsShared sh;
-  if (threadIdx.x == 0) rhs_time_setup(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
-  __syncthreads();
+  rhs_time_setup_block(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
   const int piece = SPLIT ? (int)(threadIdx.x >> 5) : -1;
   const int i = S.k_lo + (SPLIT ? blockIdx.x * 32 + (threadIdx.x & 31) : blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= S.k_hi) return;

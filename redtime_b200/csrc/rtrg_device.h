@@ -169,6 +169,11 @@ struct Profiler {
   void reset() { recs.clear(); used = 0; }
   ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
+// second stream of a handle for launch branches that may run beside the main one (launch_integrals)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
 #define RT_TIC(prof, cat, st) do { if (prof) (prof)->tic(cat, st); } while (0)
 #define RT_TOC(prof, st) do { if (prof) (prof)->toc(st); } while (0)
 #endif

@@ -215,9 +215,10 @@ struct RowX {
   double w[4];   // cubic: weights on nodes nx-1..nx+2
   double x0, x1, xq;  // linear: the two nodes
 };
-RT_HD RowX tab_row_x_prepare(const double *xs, int X, double xq) {
+// nx = tab_find(xs, X, xq), found by the caller
+RT_HD RowX tab_row_x_prepare_at(const double *xs, int X, double xq, int nx) {
   RowX r;
-  r.nx = tab_find(xs, X, xq);
+  r.nx = nx;
   r.cub = (r.nx > 0 && r.nx < X - 2);
   r.xq = xq;
   r.x0 = xs[r.nx];
@@ -231,6 +232,9 @@ RT_HD RowX tab_row_x_prepare(const double *xs, int X, double xq) {
     r.w[3] = (xq - x[0]) * (xq - x[1]) * (xq - x[2]) / (x[3] - x[0]) / (x[3] - x[1]) / (x[3] - x[2]);
   }
   return r;
+}
+RT_HD RowX tab_row_x_prepare(const double *xs, int X, double xq) {
+  return tab_row_x_prepare_at(xs, X, xq, tab_find(xs, X, xq));
 }
 RT_HD double tab_row_x_apply(const RowX &r, const double *g, long long gs = 1) {
   if (r.cub)
