@@ -85,6 +85,13 @@ def workload_name(B, nk, mode, subsample=1):
             "Latin-hypercube parameters seed 20261018" % (B, nk, sw, -(-15447 // subsample)))
 
 
+def config_dict(a, B, l2_inputs_gb):
+    """`config` of the JSON line; the reference arm prints the same dict (same workload)."""
+    return {"workload": workload_name(B, a.nk, a.mode, a.subsample), "cosmologies_per_gpu": B, "redshifts": 8,
+            "nk": a.nk, "mode": a.mode, "columns": 84 if a.print_all else 17,
+            "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2" % l2_inputs_gb}
+
+
 def metric_name(nk):
     return METRIC if nk == 128 else METRIC.replace("nk=128", "nk=%d" % nk)
 
@@ -170,6 +177,9 @@ def run_reference_arm(a, rank):
     nproc = a.ref_procs or host_cores()
     with tempfile.TemporaryDirectory() as tmp:
         dirs = reference_dirs(nproc, a.cosmologies, a.mode, a.subsample, tmp, use_library=False)
+        # bytes of the two interpolation tables of one cosmology x the batch (what the GPU arm's config states)
+        n_rows = sum(1 for l in open(os.path.join(dirs[0], "camb_transfer_z0.dat")) if l.strip() and not l.startswith("#"))
+        l2_gb = a.cosmologies * 2 * 12 * n_rows * 8 / 1e9
         for _ in range(warm):
             reference_step(dirs, binary)
         t = [reference_step(dirs, binary) for _ in range(steps)]
@@ -181,7 +191,7 @@ def run_reference_arm(a, rank):
     line = {"impl": "reference", "metric": metric_name(a.nk), "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a.cosmologies, a.nk, a.mode, a.subsample), "sample": sample},
+            "config": config_dict(a, a.cosmologies, l2_gb),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -650,9 +660,7 @@ def run_b200(a, rank, world, local_rank):
     line = {"metric": metric_name(a.nk), "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(B, a.nk, a.mode, a.subsample), "cosmologies_per_gpu": B,
-                       "redshifts": m["n_out"], "nk": a.nk, "mode": a.mode, "columns": 84 if a.print_all else 17,
-                       "l2": "256 MiB flush before every step; per-step inputs %.2f GB > L2" % m["l2_inputs_gb"]},
+            "config": config_dict(a, B, m["l2_inputs_gb"]),
             "clocks": m["clk"], "e2e": m["e2e"], "gpu_launches": m["launches"], "n_failed": n_failed,
             "roofline": roof, "cpu_baseline": cpu, "parity": parity, "modes": modes or None, "kshard": kshard, "files": files,
             "kernel_ms_in_profiled_steps": kernels}

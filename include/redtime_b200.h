@@ -96,10 +96,11 @@ int rtrg_destroy(rtrg_handle *h);
 int rtrg_set_stream(rtrg_handle *h, void *cuda_stream);
 
 /* rtrg_add_cosmology copies the tables, so the caller's buffers may be freed right after the
- * call -- EXCEPT the two big interpolation tables Tc_b and Tnu_b when both are page-locked
- * (cudaHostAlloc / cudaHostRegister / torch pin_memory): those are sent to the device directly
- * by the copy engine, without a host-side copy, and must stay valid and unchanged until
- * rtrg_prepare() has returned (and for every later rtrg_prepare() on the same batch).        */
+ * call -- EXCEPT tables that live in page-locked memory (cudaHostAlloc / cudaHostRegister / torch
+ * pin_memory): the four small ones k_T, Tc_T, Tb_T, k_b when all of them are page-locked, and the
+ * two interpolation tables Tc_b, Tnu_b when both are (and reduce_beta = 0).  Those are sent to the
+ * device directly by the copy engine, without a host-side copy, and must stay valid and unchanged
+ * until rtrg_prepare() has returned (and for every later rtrg_prepare() on the same batch).    */
 int rtrg_clear_cosmologies(rtrg_handle *h);
 int rtrg_add_cosmology(rtrg_handle *h, const rtrg_cosmology *c);
 /* the same for n cosmologies at once; the table copies run on several host threads */
