@@ -427,7 +427,7 @@ __device__ __forceinline__ double kpow_i(double k, double kinv, int p) {
 // arithmetic per row is the same.
 enum { ASM_NV = 190, ASM_MAXT = 768 };
 template <int ASM_ROWS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
     k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
                const double *__restrict__ PZb, const double *__restrict__ P3,
                const double *__restrict__ Jlo, double *__restrict__ src, double *__restrict__ raw,
@@ -465,9 +465,21 @@ __global__ void __launch_bounds__(256)
         const int nch = tb.nchunk * tb.vsplit, rb = i / BIL_R;
         const int np_rb = (rb * tb.NV + tb.NV - 1) / tb.tpb - (rb * tb.NV) / tb.tpb + 1;
         RT_ASSERT(np_rb >= 1 && np_rb <= tb.nchunk && n < N_JKERN && pair < 9);
-        for (int vs = 0; vs < tb.vsplit; vs++)
-          for (int p = 0; p < np_rb; p++)
-            x += Jpart[((((long long)e * N_JKERN + n) * nch + vs * tb.nchunk + p) * 9 + pair) * tb.nk + i];
+        // added in (split, part) order; the loads of four parts are issued together -- one memory
+        // round trip per four parts instead of one per part (x + 0.0 is exact for the padding)
+        const double *pj = Jpart + ((((long long)e * N_JKERN + n) * nch) * 9 + pair) * tb.nk + i;
+        const long long pstride = 9LL * tb.nk;
+        const int nq = tb.vsplit * np_rb;
+        for (int q0 = 0; q0 < nq; q0 += 4) {
+          double t4[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int q = q0 + u, part = (q / np_rb) * tb.nchunk + q % np_rb;
+            t4[u] = q < nq ? pj[part * pstride] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) x += t4[u];
+        }
         x *= tb.kfac[n * tb.nk + i];
       }
     } else if (v < 126) {
@@ -630,7 +642,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
   {
     RT_TIC(prof, PC_ASSEMBLE, st);
     if ((long long)B * nrows <= 2048)
-      k_assemble<4><<<dim3((nrows + 3) / 4, B), 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
+      k_assemble<4><<<dim3((nrows + 3) / 4, B), 768, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,
                                                              nrows, mask, groups);
     else
       k_assemble<16><<<dim3((nrows + 15) / 16, B), 256, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw,

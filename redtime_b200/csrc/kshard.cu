@@ -101,12 +101,13 @@ __global__ void __launch_bounds__(512) k_xch_p2p(P2pDev d, GatherPlan plan, doub
   __threadfence_system();
   __syncthreads();
   if (tid < G && tid != me) st_release_sys(d.flag(tid, slot, me), want);
-  // 3. wait for every peer's flag in my own mailbox (bounded: ~2 s)
+  // 3. wait for every peer's flag in my own mailbox (bounded: ~10 s of SM clock -- ranks may enter
+  //    rtrg_run seconds apart, e.g. after building weight tables; a peer that never comes sets err)
   if (tid < G && tid != me) {
     const unsigned long long *f = d.flag(me, slot, tid);
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < want) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > 20000000000LL) {
         atomicExch(d.err, 1);
         break;
       }
@@ -188,7 +189,7 @@ const NcclApi *nccl_api(std::string *err) {
 // EVERY rank (agreed by an all-reduce), through pack -> ncclAllGather -> unpack otherwise and for
 // bulk transfers.  A rank that dies inside a collective leaves the others blocked in NCCL: the
 // application has to ncclCommAbort / kill the job (as with any NCCL program); the P2P waits give
-// up after ~2 s and report through check().
+// up after ~10 s and report through check().
 class NcclExchange : public Exchange {
  public:
   NcclExchange(const NcclApi *api, ncclComm_t comm, int nranks, int rank, int device)
