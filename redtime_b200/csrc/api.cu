@@ -215,7 +215,7 @@ static void prof_collect(rtrg_handle *h) {
 // Bump TABLE_CACHE_VERSION whenever build_T (fastpt_tables.cc), the packing below (Tc layout,
 // BIL_R, the lag window) or this header changes: a file written by an older build is then rebuilt
 // instead of trusted.
-enum { TABLE_CACHE_VERSION = 3 };
+enum { TABLE_CACHE_VERSION = 4 };
 struct TableCacheHeader {
   char magic[8];
   int version, nk, np, nsup, n_tc, n_tlo, n_kfac, bil_r;
@@ -404,7 +404,9 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   tb.jlo = g.jlo;
   tb.nsup = g.nsup;
   tb.nloMR = g.nloMR;
-  tb.NV = g.nsup + BIL_R - 1;
+  // lag range a row block touches, in whole 8-lag DMMA tiles (nsup + BIL_R - 1 rounded up: the one
+  // or two extra lags multiply zero padding of the spectra)
+  tb.NV = (g.nsup + BIL_R - 1 + 7) / 8 * 8;
   tb.NVp = (tb.NV + BIL_R - 1) / BIL_R * BIL_R;
   tb.LP = tb.NVp + BIL_R;
   tb.NUp = nk - BIL_R + tb.NVp;
@@ -447,8 +449,11 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
           const int v = ((vv + UMIN) % np + np) % np;
           for (int uu = 0; uu < NU; uu++) {
             const int u = ((uu + UMIN) % np + np) % np;
-            // two consecutive beta-side lags share one 16-byte element: [vv/2][uu][vv&1]
-            dst[((size_t)(vv >> 1) * tb.ldT + uu) * 2 + (vv & 1)] = T[(size_t)u * np + v];
+            // 8 x 8 tiles (alpha-side lags x beta-side lags) stored in the operand order of
+            // DMMA.8x8x4: lane 4 g + t of a warp holds, as one 16-byte element, the beta-side lags
+            // 2 t and 2 t + 1 of alpha-side lag g -- the A fragments of two consecutive MMAs
+            const size_t tile = (size_t)(vv >> 3) * (tb.ldT / 8) + (uu >> 3);
+            dst[(tile * 32 + 4 * (uu & 7) + ((vv & 7) >> 1)) * 2 + (vv & 1)] = T[(size_t)u * np + v];
           }
         }
         for (int i = 0; i < nk; i++) kfac[(size_t)n * nk + i] = kf[g.nshift + i];

@@ -120,32 +120,6 @@ __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
   }
 }
 
-// ---------------------------------------------------------------------------- k_bilinear
-// Sum V values per lane over the 32 lanes of a warp by recursive halving: after the call the
-// lanes with (lane & 3) == 0 hold, in v[0..V/8), the totals of the value indices
-//   ((lane>>4)&1) * V/2 + ((lane>>3)&1) * V/4 + ((lane>>2)&1) * V/8 + i.
-// V + V/4 double shuffles instead of 5 V for V independent butterfly reductions.
-template <int V>
-__device__ __forceinline__ void warp_sum_multi(double (&v)[V], int lane) {
-  static_assert(V % 8 == 0, "V must be a multiple of 8");
-#pragma unroll
-  for (int lvl = 0; lvl < 3; lvl++) {
-    const int half = V >> (lvl + 1), bit = 16 >> lvl;
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < half; i++) {
-      const double send = up ? v[i] : v[i + half];
-      const double keep = up ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < V / 8; i++) {
-    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
-    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
-  }
-}
-
 // One work item of a k_bilinear launch: kernel n applied to the beta-side spectra cd[0..ncd).
 // Only the (kernel, spectrum) combinations the requested outputs consume are computed
 // (assembly_needs): e.g. the RHS needs A and R = all of J but only 3 of the 7 Jn0 kernels,
@@ -160,32 +134,46 @@ struct BilLaunch {
 };
 
 // ---------------------------------------------------------------------------- k_bilinear
-// A CTA always carries THREE (cosmology, beta-side spectrum) slots through the
-// same T stream, taken from consecutive entries of the list {active cosmologies} x {spectra of
-// the item}, so every T element feeds 8 rows x 3 slots = 24 DFMAs whatever the number of spectra
-// the item needs (1 for the 1-loop cache, 2 for most P_T,jm kernels, 3 inside the RHS).
-// act[0..*nact) lists the unmasked cosmologies in ascending order (compact_mask in k_extrap).
-// R: output rows per row block; TPB: threads; VC: beta-side lags per software-pipelined chunk.
+// For one kernel n, one row block (R = 8 consecutive output rows, first row i0) and one slot (a
+// cosmology with one beta-side spectrum b) the work is a small dense matrix product,
+//   S[u][r] = sum_v T'[u][v] W[v][r],   T'[u][v] = T_n[i0 + u][i0 + v],  W[v][r] = b_rev[v - r + 7],
+// over the NV alpha-side lags u and beta-side lags v the windowed spectra reach, followed by the
+// alpha-side dot products out[ab][r] = sum_u a_rev,ab[u - r + 7] S[u][r].  W is a Hankel matrix of the
+// spectrum, so nothing but the spectrum itself is staged.  The product runs on the FP64 pipe as
+// DMMA.8x8x4 (mma.sync.m8n8k4.f64): the same 64 FMA/clk/SM units as DFMA, but 256 FMAs per issued
+// instruction with 4 operand registers -- measured 37.2 TFLOP/s = 99.9 % of 148 SM x 64 x 2 x 1.965 GHz
+// against 34.3 for a register-resident DFMA loop and 25.2 for the best DFMA form of this kernel
+// (tools/dmma_probe.cu, profiles/r02_bilinear_experiments.txt).
 //
-// Work distribution.  A row block (R consecutive output rows) needs one thread per alpha-side lag,
-// NV = nsup + R - 1 of them (334 at nk = 128), each streaming its own column of the shifted T_n
-// window.  The (row block, lag) pairs of ALL row blocks are laid out on one axis, item = rb NV + tu,
-// and cut into CTAs of TPB = 256 consecutive items: 8 full warps per CTA, three CTAs = 24 warps per
-// SM at 80 registers -- every lane of every warp owns a lag (16 row blocks x 334 lags fill 20.9
-// CTAs) and the four schedulers of an SM hold six warps each.  (One CTA per row block left 18 of
-// its 352 threads idle and spread 22 warps 6/6/6/4: 68.5 % of the DFMA peak; this layout reaches
-// 73.3 %, 72.4 % with 384-thread CTAs -- tools/ab_bilinear.sh.)  A CTA touches up to three row blocks; this
-// costs nothing inside the main loop because the beta-side windows do not depend on the row block
-// (T_n is shifted along its diagonal, the spectra are not), and the epilogue reduces the lags of
-// each row block separately.  The item axis is global (independent of k-sharding), so a sharded
-// run adds the same numbers in the same order as the unsharded one.
-// Grid: (CTAs along the item axis x v_split, items of the launch, slot triples).
-template <int R, int TPB, int VC, int NS, int MINB>
+// A warp owns MT = 4 tiles of 8 alpha-side lags and NS slots: 4 NS accumulator tiles (8 x 8, two
+// doubles per lane).  Per chunk of 8 beta-side lags it issues 4 LDG.128 -- the T tiles are stored in
+// operand order, a warp reads 512 contiguous bytes per tile, prefetched one chunk ahead --, 2 NS
+// LDS.64 for the B fragments (lane (g, t): b_rev[v0 + 2 t - g + 7 + h]) and 8 NS DMMAs.  Every T
+// element fetched from L2 feeds 8 rows x NS slots FMAs.
+//
+// Work distribution.  The (row block, lag tile) pairs of ALL row blocks lie on one axis, item = rb NV +
+// lag, cut into CTAs of TPB consecutive items (TPB / 32 warps of 4 tiles).  A CTA touches up to
+// three row blocks (a warp at most two); that costs nothing inside the main loop because the B
+// fragments do not depend on the row block, and the epilogue reduces the lags of each row block
+// separately.  The item axis is global (independent of k-sharding), so a sharded run adds the same
+// numbers in the same order as the unsharded one; per-slot arithmetic does not depend on which
+// slots share a CTA.  The slots of a CTA are consecutive entries of {active cosmologies} x {spectra
+// of the item}; act[0..*nact) lists the unmasked cosmologies in ascending order (compact_mask).
+// Grid: (CTAs along the item axis x v_split, items of the launch, slot groups).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+template <int TPB, int NS, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
                double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
                const int *__restrict__ act, const int *__restrict__ nact) {
-  constexpr int NWARP = TPB / 32, NSL = 3 * NS;  // NSL: (slot, ab) sums per row
+  constexpr int R = BIL_R, VC = 8, MT = 4;        // rows per row block; lags per chunk; tiles per warp
+  constexpr int NWARP = TPB / 32, NSL = 3 * NS;   // NSL: (slot, ab) sums per row
+  static_assert(R == 8 && TPB % 32 == 0, "DMMA tiles are 8 x 8");
   const BilItem item = L.it[blockIdx.y];
   const int n = item.n, ncd = item.ncd;
   const int nslots = (*nact) * ncd;
@@ -198,10 +186,11 @@ __global__ void __launch_bounds__(TPB, MINB)
   double *s_a = sm;                     // [NS][3][LP]: the three spectra of each slot's cosmology
   double *s_red = sm + NS * 3 * tb.LP;  // [NWARP][2][NSL R]
   __shared__ __align__(8) unsigned long long mbar;
-  __shared__ int s_wrb[NWARP][2];       // row block(s) the lanes of each warp belong to
+  __shared__ int s_wrb[NWARP][2];       // row block(s) the tiles of each warp belong to
   __shared__ int s_e[NS], s_cd[NS], s_ok[NS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int LP = tb.LP, ldT = tb.ldT;
+  const int g = lane >> 2, t = lane & 3;  // DMMA fragment coordinates of this lane
+  const int LP = tb.LP;
   const uint32_t bytes = 3u * (uint32_t)LP * 8u;
 
   int e_q[NS], cd_q[NS];
@@ -221,100 +210,102 @@ __global__ void __launch_bounds__(TPB, MINB)
     for (int q = 0; q < NS; q++) tma_bulk_g2s(s_a + q * 3 * LP, Prev + (long long)e_q[q] * 3 * LP, bytes, &mbar);
   }
 
-  // this thread's (row block, alpha-side lag)
-  const int it0 = c * TPB + tid;
-  const int rb_true = it0 / tb.NV, tu = it0 - rb_true * tb.NV;
-  const bool active = rb_true >= rb_lo && rb_true < rb_hi;
-  const int rb = min(max(rb_true, rb_lo), rb_hi - 1);  // idle lanes stream a valid column, add zeros
-  const int i0 = rb * R;
-  // T stream: 16-byte elements holding two consecutive beta-side lags (LDG.128, coalesced in u)
-  const double2 *Tp = reinterpret_cast<const double2 *>(tb.Tc) + ((size_t)n * (tb.NUp / 2) + i0 / 2) * ldT + i0 + tu;
+  // the warp's tiles: global tile index -> (row block, first lag of the tile)
+  const int NVT = tb.NV >> 3, NUT = tb.ldT >> 3;
+  const int tile0 = (c * TPB + warp * 32) >> 3;
+  const size_t cstride = (size_t)NUT * 32;  // one chunk of beta-side lags further, in 16-byte elements
+  int rb_m[MT], tu_m[MT];
+  const double2 *Tp[MT];
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int gt = tile0 + m;
+    rb_m[m] = gt / NVT;
+    tu_m[m] = (gt - rb_m[m] * NVT) << 3;
+    const int rbc = min(max(rb_m[m], rb_lo), rb_hi - 1);  // idle tiles stream a valid column, are never added
+    // tile (v''/8, u''/8) with u'' = 8 rbc + tu, v'' = 8 rbc + v
+    Tp[m] = reinterpret_cast<const double2 *>(tb.Tc) +
+            (((size_t)n * (tb.NUp >> 3) + rbc) * NUT + rbc + (tu_m[m] >> 3)) * 32 + lane;
+    RT_ASSERT(n >= 0 && n < N_JKERN && 8 * rbc + tu_m[m] + 8 <= tb.ldT && 8 * rbc + tb.NVp <= tb.NUp);
+    RT_ASSERT((((size_t)n * (tb.NUp >> 3) + rbc + (tb.NVp >> 3) - 1) * NUT + rbc + (tu_m[m] >> 3)) * 64 + 63 < (size_t)tb.n_Tc);
+  }
   const double *s_c[NS];
 #pragma unroll
-  for (int q = 0; q < NS; q++) s_c[q] = s_a + (q * 3 + cd_q[q]) * LP;
-  // debug build: the T window of this thread, the shared-memory windows and the slots stay inside
-  RT_ASSERT(n >= 0 && n < N_JKERN && i0 + tu < ldT && i0 / 2 + tb.NVp / 2 <= tb.NUp / 2);
-  RT_ASSERT(((size_t)n * (tb.NUp / 2) + i0 / 2 + tb.NVp / 2 - 1) * ldT + i0 + tu < (size_t)tb.n_Tc / 2);
-  RT_ASSERT(tb.NVp + R <= LP && (R - 1) + tu < LP);
-#pragma unroll
-  for (int q = 0; q < NS; q++) RT_ASSERT(e_q[q] >= 0 && cd_q[q] >= 0 && cd_q[q] < 3);
+  for (int q = 0; q < NS; q++) {
+    s_c[q] = s_a + (q * 3 + cd_q[q]) * LP + (R - 1) + 2 * t - g;  // B fragment of this lane at lag 0
+    RT_ASSERT(e_q[q] >= 0 && cd_q[q] >= 0 && cd_q[q] < 3);
+  }
+  RT_ASSERT(tb.NVp + R <= LP && tb.NV <= tb.NVp);
 
-  double acc[R][NS];
+  double acc[MT][NS][2];
 #pragma unroll
-  for (int r = 0; r < R; r++)
+  for (int m = 0; m < MT; m++)
 #pragma unroll
-    for (int q = 0; q < NS; q++) acc[r][q] = 0.0;
+    for (int q = 0; q < NS; q++) acc[m][q][0] = acc[m][q][1] = 0.0;
   // this CTA's share of the beta-side lags (v_split > 1 shortens the serial chain of a CTA when
   // the grid is too small to fill the GPU: single cosmology, k-sharded ranks)
   const int vlen = ((tb.NVp / VC + tb.vsplit - 1) / tb.vsplit) * VC;
   const int tv_begin = vs * vlen, NVp = min(tb.NVp, tv_begin + vlen);
-  double tcur[VC], tnxt[VC];
+  double2 tcur[MT], tnxt[MT];
 #pragma unroll
-  for (int s = 0; s < VC; s += 2) {
-    double2 t2 = make_double2(0.0, 0.0);
-    if (tv_begin < tb.NVp) t2 = __ldg(Tp + (size_t)((tv_begin + s) / 2) * ldT);  // (an empty split adds zeros)
-    tcur[s] = t2.x;
-    tcur[s + 1] = t2.y;
+  for (int m = 0; m < MT; m++) {
+    tcur[m] = make_double2(0.0, 0.0);
+    if (tv_begin < tb.NVp) tcur[m] = __ldg(Tp[m] + (size_t)(tv_begin >> 3) * cstride);  // (an empty split adds zeros)
+    tnxt[m] = tcur[m];
   }
 
   mbar_wait(&mbar, 0);
 
-  constexpr int NW = (VC + R) / 2;
   for (int tv0 = tv_begin; tv0 < NVp; tv0 += VC) {
     if (tv0 + VC < NVp) {
-      const double2 *Tn = Tp + (size_t)((tv0 + VC) / 2) * ldT;
 #pragma unroll
-      for (int s = 0; s < VC; s += 2) {
-        const double2 t2 = __ldg(Tn + (size_t)(s / 2) * ldT);
-        tnxt[s] = t2.x;
-        tnxt[s + 1] = t2.y;
-      }
+      for (int m = 0; m < MT; m++) tnxt[m] = __ldg(Tp[m] + (size_t)((tv0 + VC) >> 3) * cstride);
     }
 #pragma unroll
     for (int q = 0; q < NS; q++) {
-      double w[2 * NW];
-      const double2 *wp = reinterpret_cast<const double2 *>(s_c[q] + tv0);
+      const double b0 = s_c[q][tv0], b1 = s_c[q][tv0 + 1];
 #pragma unroll
-      for (int i = 0; i < NW; i++) {
-        const double2 v = wp[i];
-        w[2 * i] = v.x;
-        w[2 * i + 1] = v.y;
-      }
-      // window-major order: consecutive DFMAs share w[j]; per accumulator the lags still arrive
-      // in ascending order
+      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].x, b0);  // lags tv0 + 0, 2, 4, 6
 #pragma unroll
-      for (int j = 0; j < VC + R - 1; j++)
-#pragma unroll
-        for (int s = 0; s < VC; s++) {
-          const int r = s + R - 1 - j;
-          if (r >= 0 && r < R) acc[r][q] = fma(tcur[s], w[j], acc[r][q]);
-        }
+      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].y, b1);  // lags tv0 + 1, 3, 5, 7
     }
 #pragma unroll
-    for (int s = 0; s < VC; s++) tcur[s] = tnxt[s];
+    for (int m = 0; m < MT; m++) tcur[m] = tnxt[m];
   }
 
-  // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r] * S_u[r], the sum running over the
-  // lags of ONE row block.  A warp holds lanes of one row block, or of two when it straddles a
-  // block boundary (about one warp in ten): side 0 = the block of lane 0, side 1 = that of lane 31.
-  static_assert(R == 8, "the epilogue reduction is written for 8 rows per row block");
-  const int rbA = __shfl_sync(0xffffffffu, rb_true, 0), rbB = __shfl_sync(0xffffffffu, rb_true, 31);
+  // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r + 7] * S[u][r], the sum running over the
+  // lags of ONE row block.  Lane (g, t) holds S[tu_m + g][2 t] and S[tu_m + g][2 t + 1] of its tiles.
+  // A warp holds tiles of one row block, or of two when it straddles a block boundary: side 0 = the
+  // block of tile 0, side 1 = that of tile 3.
+  const int rbA = rb_m[0], rbB = rb_m[MT - 1];
   const int nside = (rbA == rbB) ? 1 : 2;
   if (lane == 0) s_wrb[warp][0] = rbA, s_wrb[warp][1] = (nside == 2) ? rbB : -1;
   const int nab = L.replicate ? 1 : 3;
 #pragma unroll
   for (int q = 0; q < NS; q++) {
     for (int ab = 0; ab < nab; ab++) {
+      const double *ap = s_a + (q * 3 + ab) * LP + (R - 1) + g - 2 * t;
       for (int side = 0; side < nside; side++) {
-        const bool mine = active && rb_true == (side ? rbB : rbA);
-        double prod[R];
+        const int rbs = side ? rbB : rbA;
+        double p0 = 0.0, p1 = 0.0;
+        if (rbs >= rb_lo && rbs < rb_hi) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const double m = mine ? s_a[(q * 3 + ab) * LP + (R - 1) + tu - r] : 0.0;
-          prod[r] = m * acc[r][q];
+          for (int m = 0; m < MT; m++)
+            if (rb_m[m] == rbs) {
+              RT_ASSERT((R - 1) + g - 2 * t + tu_m[m] - 1 >= 0 && (R - 1) + g - 2 * t + tu_m[m] < LP);
+              p0 = fma(ap[tu_m[m]], acc[m][q][0], p0);
+              p1 = fma(ap[tu_m[m] - 1], acc[m][q][1], p1);
+            }
         }
-        warp_sum_multi<R>(prod, lane);
-        if ((lane & 3) == 0) s_red[(warp * 2 + side) * (NSL * R) + (q * 3 + ab) * R + (lane >> 2)] = prod[0];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+          p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+        }
+        if (g == 0) {
+          double *dst = s_red + (warp * 2 + side) * (NSL * R) + (q * 3 + ab) * R + 2 * t;
+          dst[0] = p0;
+          dst[1] = p1;
+        }
       }
     }
   }
@@ -519,14 +510,13 @@ __global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
 
 // ---------------------------------------------------------------------------- launchers
 // Tuning variants of the bilinear kernel (threads per CTA, slots per CTA, CTAs per SM), selected
-// once per process by RTRG_BIL_VARIANT; 0 is the production configuration (256 threads, 3 slots,
-// 3 CTAs per SM).  Results do not
-// depend on the slot count; they depend on the threads per CTA at round-off level (which lags
-// share a partial sum).
+// once per process by RTRG_BIL_VARIANT; 0 is the production configuration.  Results do not depend on
+// the slot count; they depend on the threads per CTA at round-off level (which lags share a
+// partial sum).
 struct BilVariant {
   int tpb, ns;
 };
-static const BilVariant kBilVariants[] = {{256, 3}, {320, 3}, {256, 3}, {384, 2}, {256, 4}, {320, 4}, {384, 3}};
+static const BilVariant kBilVariants[] = {{256, 3}, {256, 4}, {256, 2}, {128, 3}, {128, 4}, {256, 6}, {512, 3}};
 static int bil_variant_index() {
   static const int v = [] {
     const char *e = std::getenv("RTRG_BIL_VARIANT");
@@ -543,13 +533,13 @@ size_t bilinear_smem_bytes(const IntegralTabs &tb) {
 template <class F>
 static auto bil_dispatch(F &&f) {
   switch (bil_variant_index()) {
-    case 1: return f(k_bilinear<BIL_R, 320, 8, 3, 2>, 320, 3);
-    case 2: return f(k_bilinear<BIL_R, 256, 8, 3, 2>, 256, 3);
-    case 3: return f(k_bilinear<BIL_R, 384, 8, 2, 2>, 384, 2);
-    case 4: return f(k_bilinear<BIL_R, 256, 8, 4, 2>, 256, 4);
-    case 5: return f(k_bilinear<BIL_R, 320, 8, 4, 2>, 320, 4);
-    case 6: return f(k_bilinear<BIL_R, 384, 8, 3, 2>, 384, 3);
-    default: return f(k_bilinear<BIL_R, 256, 8, 3, 3>, 256, 3);
+    case 1: return f(k_bilinear<256, 4, 2>, 256, 4);
+    case 2: return f(k_bilinear<256, 2, 3>, 256, 2);
+    case 3: return f(k_bilinear<128, 3, 4>, 128, 3);
+    case 4: return f(k_bilinear<128, 4, 4>, 128, 4);
+    case 5: return f(k_bilinear<256, 6, 1>, 256, 6);
+    case 6: return f(k_bilinear<512, 3, 1>, 512, 3);
+    default: return f(k_bilinear<256, 3, 2>, 256, 3);
   }
 }
 

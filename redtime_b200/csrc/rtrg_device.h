@@ -15,7 +15,8 @@
 //                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
 //   inputs             in     [sum over cosmologies of 3 nT + n_z + n_kb + 2 n_z n_kb]
 //                                                    raw CAMB columns, transformed in place
-//   weight tables      Tc     [14][NUp/2][ldT][2]    compact circulant kernels (L2 resident)
+//   weight tables      Tc     [14][NUp/8][ldT/8][32][2]  compact circulant kernels as 8 x 8 tiles in
+//                                                    DMMA operand order (L2 resident)
 #pragma once
 #include "rtrg_math.h"
 #ifdef __CUDACC__
@@ -48,7 +49,7 @@ enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Co
 
 struct IntegralTabs {
   int nk, np, nshift, jlo, nsup, nloMR;
-  int NV;      // nsup + BIL_R - 1 : lag range a row block touches
+  int NV;      // nsup + BIL_R - 1 rounded up to whole 8-lag tiles: lag range a row block touches
   int NVp;     // NV rounded up to a multiple of BIL_R
   int LP;      // padded length of one reversed spectrum (even)
   int NUp;     // rows of the compact kernel table (>= nk + NVp)
@@ -59,7 +60,7 @@ struct IntegralTabs {
   int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
-  const double *Tc;    // [14][NUp/2][ldT][2]  Tc[n][v''/2][u''][v''&1] = T_n[u][v] (16-byte pairs in v)
+  const double *Tc;    // [14][NUp/8][ldT/8][32][2]  tile (v''/8, u''/8), lane 4 (u''&7) + (v''&7)/2, half v''&1 = T_n[u][v]
   const double *Tlo;   // [nsup][nsup]    kernel 0 at the low-k row nloMR (reversed indices)
   const double *kfac;  // [14][nk]
   const double *G;     // [7][2np-1]
