@@ -166,14 +166,15 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-template <int TPB, int NS, int MINB>
-__global__ void __launch_bounds__(TPB, MINB)
+template <int NWARP, int MT, int NS, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
                double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
-               const int *__restrict__ act, const int *__restrict__ nact) {
-  constexpr int R = BIL_R, VC = 8, MT = 4;        // rows per row block; lags per chunk; tiles per warp
-  constexpr int NWARP = TPB / 32, NSL = 3 * NS;   // NSL: (slot, ab) sums per row
-  static_assert(R == 8 && TPB % 32 == 0, "DMMA tiles are 8 x 8");
+               const int *__restrict__ act, const int *__restrict__ nact, int dephase) {
+  constexpr int R = BIL_R, VC = 8;                  // rows per row block; lags per chunk
+  constexpr int IPC = NWARP * MT * 8;               // items (alpha-side lags) per CTA
+  constexpr int NSL = 3 * NS;                       // (slot, ab) sums per row
+  static_assert(R == 8, "DMMA tiles are 8 x 8");
   const BilItem item = L.it[blockIdx.y];
   const int n = item.n, ncd = item.ncd;
   const int nslots = (*nact) * ncd;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 
   // the warp's tiles: global tile index -> (row block, first lag of the tile)
   const int NVT = tb.NV >> 3, NUT = tb.ldT >> 3;
-  const int tile0 = (c * TPB + warp * 32) >> 3;
+  const int tile0 = (c * IPC + warp * (MT * 8)) >> 3;
   const size_t cstride = (size_t)NUT * 32;  // one chunk of beta-side lags further, in 16-byte elements
   int rb_m[MT], tu_m[MT];
   const double2 *Tp[MT];
@@ -260,75 +261,111 @@ __global__ void __launch_bounds__(TPB, MINB)
 #pragma unroll
       for (int m = 0; m < MT; m++) tnxt[m] = __ldg(Tp[m] + (size_t)((tv0 + VC) >> 3) * cstride);
     }
+    double bf[NS][2];
 #pragma unroll
-    for (int q = 0; q < NS; q++) {
-      const double b0 = s_c[q][tv0], b1 = s_c[q][tv0 + 1];
+    for (int q = 0; q < NS; q++) bf[q][0] = s_c[q][tv0], bf[q][1] = s_c[q][tv0 + 1];
+    // (half, slot, tile) order: an accumulator is touched again 4 NS DMMAs later
 #pragma unroll
-      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].x, b0);  // lags tv0 + 0, 2, 4, 6
+    for (int q = 0; q < NS; q++)
 #pragma unroll
-      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].y, b1);  // lags tv0 + 1, 3, 5, 7
-    }
+      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].x, bf[q][0]);  // lags tv0 + 0, 2, 4, 6
+#pragma unroll
+    for (int q = 0; q < NS; q++)
+#pragma unroll
+      for (int m = 0; m < MT; m++) dmma884(acc[m][q], tcur[m].y, bf[q][1]);  // lags tv0 + 1, 3, 5, 7
 #pragma unroll
     for (int m = 0; m < MT; m++) tcur[m] = tnxt[m];
   }
 
+  if (dephase == -1) {  // experiment: main loop only
+    double sacc = 0;
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int q = 0; q < NS; q++) sacc += acc[m][q][0] + acc[m][q][1];
+    if (sacc == 123.456) Jpart[0] = sacc;
+    return;
+  }
   // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r + 7] * S[u][r], the sum running over the
   // lags of ONE row block.  Lane (g, t) holds S[tu_m + g][2 t] and S[tu_m + g][2 t + 1] of its tiles.
   // A warp holds tiles of one row block, or of two when it straddles a block boundary: side 0 = the
   // block of tile 0, side 1 = that of tile 3.
+  // The FP64 instructions of this part queue behind the DMMAs of the warps that are still in their
+  // main loops, so what counts is the length of its dependency chains: the 2 NSL partial sums of a
+  // lane are built as independent chains (one DFMA per tile each), then reduced over the 8 lane
+  // groups by recursive halving (3 exchange levels, 7/8 NSL' shuffle + add pairs in all).
   const int rbA = rb_m[0], rbB = rb_m[MT - 1];
   const int nside = (rbA == rbB) ? 1 : 2;
   if (lane == 0) s_wrb[warp][0] = rbA, s_wrb[warp][1] = (nside == 2) ? rbB : -1;
   const int nab = L.replicate ? 1 : 3;
+  constexpr int NPV = (2 * NSL + 7) / 8 * 8;  // values per lane, padded to a multiple of 8
+  for (int side = 0; side < nside; side++) {
+    const int rbs = side ? rbB : rbA;
+    if (rbs < rb_lo || rbs >= rb_hi) continue;  // (never summed: the row block is another rank's)
+    double pv[NPV];
 #pragma unroll
-  for (int q = 0; q < NS; q++) {
-    for (int ab = 0; ab < nab; ab++) {
-      const double *ap = s_a + (q * 3 + ab) * LP + (R - 1) + g - 2 * t;
-      for (int side = 0; side < nside; side++) {
-        const int rbs = side ? rbB : rbA;
-        double p0 = 0.0, p1 = 0.0;
-        if (rbs >= rb_lo && rbs < rb_hi) {
+    for (int i = 0; i < NPV; i++) pv[i] = 0.0;
 #pragma unroll
-          for (int m = 0; m < MT; m++)
-            if (rb_m[m] == rbs) {
-              RT_ASSERT((R - 1) + g - 2 * t + tu_m[m] - 1 >= 0 && (R - 1) + g - 2 * t + tu_m[m] < LP);
-              p0 = fma(ap[tu_m[m]], acc[m][q][0], p0);
-              p1 = fma(ap[tu_m[m] - 1], acc[m][q][1], p1);
-            }
-        }
+    for (int m = 0; m < MT; m++) {
+      if (rb_m[m] != rbs) continue;
+      const double *ap = s_a + (R - 1) + g - 2 * t + tu_m[m];
+      RT_ASSERT((R - 1) + g - 2 * t + tu_m[m] - 1 >= 0 && (R - 1) + g - 2 * t + tu_m[m] < LP);
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-          p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      for (int q = 0; q < NS; q++)
+#pragma unroll
+        for (int ab = 0; ab < 3; ab++) {
+          const double2 w = make_double2(ap[(q * 3 + ab) * LP], ap[(q * 3 + ab) * LP - 1]);
+          pv[(q * 3 + ab) * 2] = fma(w.x, acc[m][q][0], pv[(q * 3 + ab) * 2]);
+          pv[(q * 3 + ab) * 2 + 1] = fma(w.y, acc[m][q][1], pv[(q * 3 + ab) * 2 + 1]);
         }
-        if (g == 0) {
-          double *dst = s_red + (warp * 2 + side) * (NSL * R) + (q * 3 + ab) * R + 2 * t;
-          dst[0] = p0;
-          dst[1] = p1;
-        }
+    }
+    // after level l (lane bit 16 >> l) a lane keeps the half of its values selected by that bit:
+    // lane group (b16, b8, b4) ends with the totals of values b16 NPV/2 + b8 NPV/4 + b4 NPV/8 + i
+#pragma unroll
+    for (int lvl = 0; lvl < 3; lvl++) {
+      const int half = NPV >> (lvl + 1), bit = 16 >> lvl;
+      const bool up = (lane & bit) != 0;
+#pragma unroll
+      for (int i = 0; i < half; i++) {
+        const double send = up ? pv[i] : pv[i + half];
+        const double keep = up ? pv[i + half] : pv[i];
+        pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
       }
+    }
+    const int v0 = ((lane >> 4) & 1) * (NPV / 2) + ((lane >> 3) & 1) * (NPV / 4) + ((lane >> 2) & 1) * (NPV / 8);
+#pragma unroll
+    for (int i = 0; i < NPV / 8; i++) {
+      const int v = v0 + i;  // = (q 3 + ab) 2 + (r & 1), r = 2 t + (r & 1)
+      if (v < 2 * NSL) s_red[(warp * 2 + side) * (NSL * R) + (v >> 1) * R + 2 * t + (v & 1)] = pv[i];
     }
   }
   __syncthreads();
   // one thread per (row block of this CTA, slot, ab, row): add the warps' partial sums in warp
   // order and store this CTA's part of the row block
-  const int rb_first = (c * TPB) / tb.NV, nrbl = (c * TPB + TPB - 1) / tb.NV - rb_first + 1;
+  const int rb_first = (c * IPC) / tb.NV, nrbl = (c * IPC + IPC - 1) / tb.NV - rb_first + 1;
   const int nch = tb.nchunk * tb.vsplit;
-  for (int idx = tid; idx < nrbl * NSL * R; idx += TPB) {
+  for (int idx = tid; idx < nrbl * NSL * R; idx += NWARP * 32) {
     const int rbl = idx / (NSL * R), x = idx - rbl * (NSL * R), rbx = rb_first + rbl;
     if (rbx < rb_lo || rbx >= rb_hi) continue;
     const int slot = x / R, r = x - slot * R, q = slot / 3, ab = slot - 3 * q;
     const int e = s_e[q];
     // Jn0 only feeds the RSD terms (rt:804): cosmologies without them keep their old entries
     if (!s_ok[q] || ab >= nab || (n >= 7 && !cosmo[e].sw_pr)) continue;
-    double s = 0.0;
-#pragma unroll 1
+    // the warps' parts in a fixed pairwise order (x + 0.0 is exact for the warps of other blocks)
+    double sw[NWARP];
+#pragma unroll
     for (int wv = 0; wv < NWARP; wv++) {
-      if (s_wrb[wv][0] == rbx) s += s_red[(wv * 2) * (NSL * R) + x];
-      if (s_wrb[wv][1] == rbx) s += s_red[(wv * 2 + 1) * (NSL * R) + x];
+      const double s0 = (s_wrb[wv][0] == rbx) ? s_red[(wv * 2) * (NSL * R) + x] : 0.0;
+      const double s1 = (s_wrb[wv][1] == rbx) ? s_red[(wv * 2 + 1) * (NSL * R) + x] : 0.0;
+      sw[wv] = s0 + s1;
     }
-    const int part = vs * tb.nchunk + (c - (rbx * tb.NV) / TPB);
-    RT_ASSERT(part >= 0 && part < nch && c - (rbx * tb.NV) / TPB < tb.nchunk && rbx * R + r < tb.nk);
+#pragma unroll
+    for (int step = 1; step < NWARP; step <<= 1)
+#pragma unroll
+      for (int wv = 0; wv + step < NWARP; wv += 2 * step) sw[wv] += sw[wv + step];
+    const double s = sw[0];
+    const int part = vs * tb.nchunk + (c - (rbx * tb.NV) / IPC);
+    RT_ASSERT(part >= 0 && part < nch && c - (rbx * tb.NV) / IPC < tb.nchunk && rbx * R + r < tb.nk);
     double *dst = Jpart + (((long long)e * N_JKERN + n) * nch + part) * 9 * tb.nk + rbx * R + r;
     if (L.replicate) {
 #pragma unroll
@@ -514,9 +551,10 @@ __global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
 // the slot count; they depend on the threads per CTA at round-off level (which lags share a
 // partial sum).
 struct BilVariant {
-  int tpb, ns;
+  int nwarp, mt, ns;
+  int ipc() const { return nwarp * mt * 8; }  // items (alpha-side lags) per CTA
 };
-static const BilVariant kBilVariants[] = {{256, 3}, {256, 4}, {256, 2}, {128, 3}, {128, 4}, {256, 6}, {512, 3}};
+static const BilVariant kBilVariants[] = {{8, 4, 3}, {8, 2, 3}, {16, 2, 3}, {4, 4, 3}, {8, 2, 4}, {4, 2, 3}, {16, 1, 3}};
 static int bil_variant_index() {
   static const int v = [] {
     const char *e = std::getenv("RTRG_BIL_VARIANT");
@@ -525,21 +563,25 @@ static int bil_variant_index() {
   }();
   return v;
 }
-int bilinear_tpb() { return kBilVariants[bil_variant_index()].tpb; }
+int bilinear_tpb() { return kBilVariants[bil_variant_index()].ipc(); }
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
   const BilVariant v = kBilVariants[bil_variant_index()];
-  return (size_t)(3 * v.ns * tb.LP + (v.tpb / 32) * 2 * 3 * v.ns * BIL_R) * sizeof(double);
+  static const size_t extra = [] {
+    const char *e = std::getenv("RTRG_BIL_EXTRA_SMEM");
+    return e ? (size_t)std::atoi(e) : (size_t)0;
+  }();
+  return extra + (size_t)(3 * v.ns * tb.LP + v.nwarp * 2 * 3 * v.ns * BIL_R) * sizeof(double);
 }
 template <class F>
 static auto bil_dispatch(F &&f) {
   switch (bil_variant_index()) {
-    case 1: return f(k_bilinear<256, 4, 2>, 256, 4);
-    case 2: return f(k_bilinear<256, 2, 3>, 256, 2);
-    case 3: return f(k_bilinear<128, 3, 4>, 128, 3);
-    case 4: return f(k_bilinear<128, 4, 4>, 128, 4);
-    case 5: return f(k_bilinear<256, 6, 1>, 256, 6);
-    case 6: return f(k_bilinear<512, 3, 1>, 512, 3);
-    default: return f(k_bilinear<256, 3, 2>, 256, 3);
+    case 1: return f(k_bilinear<8, 2, 3, 4>, kBilVariants[1]);
+    case 2: return f(k_bilinear<16, 2, 3, 2>, kBilVariants[2]);
+    case 3: return f(k_bilinear<4, 4, 3, 4>, kBilVariants[3]);
+    case 4: return f(k_bilinear<8, 2, 4, 3>, kBilVariants[4]);
+    case 5: return f(k_bilinear<4, 2, 3, 8>, kBilVariants[5]);
+    case 6: return f(k_bilinear<16, 1, 3, 4>, kBilVariants[6]);
+    default: return f(k_bilinear<8, 4, 3, 2>, kBilVariants[0]);
   }
 }
 
@@ -597,10 +639,15 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     for (int i = 0; i < nitems; i++) maxncd = std::max(maxncd, (int)L.it[i].ncd);
     // CTAs along the global (row block, lag) axis that hold lags of this rank's row blocks
     const int rb_lo = row0 / BIL_R, rb_hi = (row0 + nrows) / BIL_R;
-    bil_dispatch([&](auto kern, int tpb, int ns) {
-      const int c_lo = (rb_lo * tb.NV) / tpb, c_hi = (rb_hi * tb.NV - 1) / tpb;
+    bil_dispatch([&](auto kern, const BilVariant &v) {
+      const int ipc = v.ipc(), ns = v.ns, tpb = v.nwarp * 32;
+      const int c_lo = (rb_lo * tb.NV) / ipc, c_hi = (rb_hi * tb.NV - 1) / ipc;
       dim3 g((c_hi - c_lo + 1) * tb.vsplit, nitems, (B * maxncd + ns - 1) / ns);
-      kern<<<g, tpb, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo, rb_hi, c_lo, S.act, S.nact);
+      static const int dephase = [] {
+        const char *e = std::getenv("RTRG_BIL_DEPHASE");
+        return e ? std::atoi(e) : 0;
+      }();
+      kern<<<g, tpb, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo, rb_hi, c_lo, S.act, S.nact, dephase);
       return 0;
     });
     launches++;
@@ -651,7 +698,7 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 
 int integrals_configure(const IntegralTabs &tb) {
   // opt in to the dynamic shared memory the bilinear kernel needs on large grids
-  return bil_dispatch([&](auto kern, int, int) {
+  return bil_dispatch([&](auto kern, const BilVariant &) {
     return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bilinear_smem_bytes(tb));
   });
 }
