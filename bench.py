@@ -17,7 +17,7 @@ Time-RG evolution with the batched RKF45 stepper + output tables at 8 redshifts)
           batch i+1 is staged, uploaded and initialised while batch i evolves).
   roofline     : the dominant kernel (k_bilinear, FP64 FMA pipe): algorithmic FLOP of all its
                  launches / its CUDA-event time (extra steps with per-kernel event timing),
-                 against the DFMA peak measured live.
+                 against the FP64 pipe peak (DMMA loop) measured live.
   cpu_baseline : oracle/_ref/redTime (the UNMODIFIED reference sources + mini-GSL shim) as one
                  single-thread process per host core on the FIRST cosmologies of rank 0's batch.
   parity       : those oracle tables against the GPU tables of the same cosmologies (taken from the
@@ -611,7 +611,7 @@ def run_b200(a, rank, world, local_rank):
     if not a.no_modes and a.mode == "1loop" and a.nk == 128 and not a.print_all:
         for name, nk, mode, Bm in (("full_trg", 128, "full", 256), ("nk256", 256, "1loop", 256)):
             r = measure_batch(a, comm, rank, world, local_rank, Bm, nk, mode, 3, 1, not a.no_e2e, prof_steps=1)
-            peak_m = rt.dfma_peak_tflops(local_rank, 0.2) if rank == 0 else None
+            peak_m = rt.dmma_peak_tflops(local_rank, 0.2) if rank == 0 else None
             modes[name] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
                            "metric": metric_name(nk) + (", full Time-RG" if mode == "full" else ""),
                            "workload": workload_name(Bm, nk, mode, a.subsample), "cosmologies_per_gpu": Bm, "steps": 3,
@@ -628,7 +628,8 @@ def run_b200(a, rank, world, local_rank):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel
-    peak = rt.dfma_peak_tflops(local_rank, 0.5)
+    peak = rt.dmma_peak_tflops(local_rank, 0.5)
+    peak_dfma = rt.dfma_peak_tflops(local_rank, 0.3)
     sm_clk = 1.965e9
     traffic, traffic_src = ncu_traffic()
     roof = {"bound": "fp64", "kernel": "k_bilinear", "achieved": m["achieved"], "peak": peak, "unit": "TFLOP/s",
@@ -637,8 +638,11 @@ def run_b200(a, rank, world, local_rank):
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed from %s (ncu --set full of "
                             "tools/bench_integrals.py 64: 64 cosmologies x 42 matvec sets = 74.3 GFLOP algorithmic; the "
                             "23.7 MB weight tables stream from L2, DRAM sees them once)" % os.path.relpath(traffic_src, ROOT),
-            "peak_source": "DFMA loop measured live by rtrg_bench_dfma (MEASURED_PEAKS.json has no FP64 figure); "
-                           "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = %.1f TFLOP/s" % (148 * 64 * 2 * sm_clk * 1e-12),
+            "peak_source": "register-resident DMMA.8x8x4 loop measured live by rtrg_bench_dmma (MEASURED_PEAKS.json has no "
+                           "FP64 figure); a scalar DFMA loop (rtrg_bench_dfma) reaches %.2f; nominal 148 SM x 64 FMA/clk "
+                           "x 2 x 1.965 GHz = %.1f TFLOP/s.  k_bilinear issues its FMAs as DMMA.8x8x4: the same FP64 "
+                           "units, ncu books them under sm__pipe_tensor_subpipe_dmma_cycles_active"
+                           % (peak_dfma, 148 * 64 * 2 * sm_clk * 1e-12),
             "launches": m["n_bil"], "avg_launch_ms": m["ms_bil"] / max(m["n_bil"], 1),
             "timed": "CUDA events around every launch in %d extra steps (per-kernel events switch the graph replay "
                      "off; those steps took %.2f ms each against %.2f ms for the graph-launched timed steps)"
@@ -759,7 +763,7 @@ def kshard_record(a, comm, rank, world, local_rank, steps, warm):
     err = np.max(np.abs(tables[0] - ref) / (np.abs(ref) + 1e-300), axis=(0, 1)) if a.subsample == 1 else None
     grid = rt.grid_info(nk)
     n_bil, ms_bil = prof["k_bilinear"]
-    peak = rt.dfma_peak_tflops(local_rank, 0.3)
+    peak = rt.dmma_peak_tflops(local_rank, 0.3)
     # this rank's share: matvec sets x its nk/world rows
     achieved = flops_per_matvec_set(grid, nk) / world * sets_per_step / (ms_bil * 1e-3) * 1e-12 if ms_bil else 0.0
     return {"metric": "cosmology*redshift outputs/sec, ONE nk=256 high-accuracy full-TRG cosmology, k-sharded",

@@ -205,8 +205,11 @@ int rtrg_profile_query(const rtrg_handle *h, int cat, long long *n_launches, dou
  * identical != 0 uses the identical-spectra shortcut of the 1-loop cache.  Results go to the
  * scratch source buffer only.                                                            */
 int rtrg_bench_integrals(rtrg_handle *h, int reps, int groups, int identical);
-/* FP64 FMA pipe peak of `device` in TFLOP/s (register-resident DFMA loop, best launch over
- * about `seconds` of device time): the roofline denominator of the integral kernels.    */
+/* FP64 pipe peak of `device` in TFLOP/s, best launch over about `seconds` of device time.
+ * rtrg_bench_dmma: register-resident DMMA.8x8x4 loop (the instruction the bilinear kernel runs on;
+ * reaches the nominal 64 FMA/clk/SM) -- the roofline denominator of the integral kernels.
+ * rtrg_bench_dfma: register-resident scalar DFMA loop (about 92 % of the nominal rate).   */
+int rtrg_bench_dmma(int device, double seconds, double *tflops);
 int rtrg_bench_dfma(int device, double seconds, double *tflops);
 
 /* ---- stage-level hooks with the reference's array layouts (parity tests) ---------- */

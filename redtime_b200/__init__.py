@@ -8,9 +8,9 @@ library or a CUDA device is missing.
 """
 from .binding import (RedTimeB200, RtrgError, Config, load_library, library_path,
                       read_run_dir, grid_info, table_T, table_G, table_windows, table_extrap,
-                      assembly_terms, print_result, dfma_peak_tflops, kshard_nccl_id,
+                      assembly_terms, print_result, dfma_peak_tflops, dmma_peak_tflops, kshard_nccl_id,
                       LoopbackGroup, pack_cosmologies, Pipeline)
 
 __all__ = ["RedTimeB200", "RtrgError", "Config", "load_library", "library_path",
            "read_run_dir", "grid_info", "table_T", "table_G", "table_windows", "table_extrap",
-           "assembly_terms", "print_result", "dfma_peak_tflops", "kshard_nccl_id", "LoopbackGroup", "pack_cosmologies", "Pipeline"]
+           "assembly_terms", "print_result", "dfma_peak_tflops", "dmma_peak_tflops", "kshard_nccl_id", "LoopbackGroup", "pack_cosmologies", "Pipeline"]

@@ -77,6 +77,7 @@ def load_library():
     lib.rtrg_profile_name.restype = C.c_char_p
     lib.rtrg_profile_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _dp]
     lib.rtrg_bench_dfma.argtypes = [C.c_int, C.c_double, _dp]
+    lib.rtrg_bench_dmma.argtypes = [C.c_int, C.c_double, _dp]
     lib.rtrg_bench_integrals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.rtrg_kshard_nccl_id.argtypes = [C.c_char_p]
     lib.rtrg_kshard_init_nccl.argtypes = [C.c_void_p, C.c_char_p]
@@ -322,10 +323,19 @@ class Pipeline:
 
 
 def dfma_peak_tflops(device=0, seconds=0.5):
-    """Measured FP64 FMA peak of the device (TFLOP/s)."""
+    """Measured rate of a register-resident scalar DFMA loop (TFLOP/s)."""
     lib = load_library()
     t = C.c_double()
     _check(lib.rtrg_bench_dfma(int(device), float(seconds), C.byref(t)))
+    return t.value
+
+
+def dmma_peak_tflops(device=0, seconds=0.5):
+    """Measured FP64 pipe peak of the device (TFLOP/s): a register-resident DMMA.8x8x4 loop, the
+    instruction the bilinear kernel runs on."""
+    lib = load_library()
+    t = C.c_double()
+    _check(lib.rtrg_bench_dmma(int(device), float(seconds), C.byref(t)))
     return t.value
 
 

@@ -17,9 +17,9 @@ h = rt.RedTimeB200(nk=nk)
 h.add_cosmologies(wl.make_cosmologies(B, base))
 h.prepare()
 g = rt.grid_info(nk)
-peak = rt.dfma_peak_tflops(0, 0.3)
+peak = rt.dmma_peak_tflops(0, 0.3)
 flop_set = nk * (2.0 * g["nsup"] ** 2 + 6.0 * g["nsup"])
-print("B=%d nk=%d  measured DFMA peak %.2f TFLOP/s" % (B, nk, peak))
+print("B=%d nk=%d  measured FP64 pipe peak (DMMA loop) %.2f TFLOP/s" % (B, nk, peak))
 row, src, idx, kpw, cf = rt.assembly_terms()
 
 

@@ -127,6 +127,62 @@ __global__ void __launch_bounds__(256) k_peak(double *out, int iters, double a, 
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// DMMA stream with KD scalar DFMAs (independent chains) after every 24 DMMAs: what a scalar FP64
+// instruction costs the pipe when it is interleaved with DMMAs.
+template <int KD>
+__global__ void __launch_bounds__(256) k_dmma_mix(double *out, int iters, double a0, double b0) {
+  double c[4][3][2];
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int q = 0; q < 3; q++) c[m][q][0] = threadIdx.x + m, c[m][q][1] = q;
+  double a[4][2], b[3][2], x[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) x[i] = threadIdx.x + i;
+#pragma unroll
+  for (int m = 0; m < 4; m++) a[m][0] = a0 + m * 1e-9 + threadIdx.x * 1e-12, a[m][1] = a0 - m * 1e-9;
+#pragma unroll
+  for (int q = 0; q < 3; q++) b[q][0] = b0 + q * 1e-9, b[q][1] = b0 - q * 1e-9;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) mma884(c[m][q], a[m][h], b[q][h]);
+#pragma unroll
+      for (int i = 0; i < KD; i++) x[i] = fma(x[i], a0, b0);
+      const double t0 = a[0][0];
+#pragma unroll
+      for (int m = 0; m < 3; m++) a[m][0] = a[m + 1][0];
+      a[3][0] = t0;
+      const double t1 = b[0][1];
+      b[0][1] = b[1][1], b[1][1] = b[2][1], b[2][1] = t1;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int q = 0; q < 3; q++) s += c[m][q][0] + c[m][q][1];
+#pragma unroll
+  for (int i = 0; i < 24; i++) s += x[i];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <class F>
+static double time_ms(F f);
+template <int KD>
+static void run_mix(double *out, int sms) {
+  const int ctas = sms * 2, iters = 2000;
+  const double ms = time_ms([&] { k_dmma_mix<KD><<<ctas, 256>>>(out, iters, 0.999999, 1e-9); });
+  const double flop = 512.0 * 4 * 24 * iters * (double)ctas * 8;
+  std::printf("24 DMMA + %2d DFMA, 16 warps/SM: %7.2f TFLOP/s in DMMAs, %.3f ms\n", KD, flop / ms * 1e-9, ms);
+}
+
 template <class F>
 static double time_ms(F f) {
   cudaEvent_t e0, e1;
@@ -179,12 +235,24 @@ int main() {
     const double flop = 512.0 * 4 * 2 * 12 * iters * (double)ctas * 8;
     std::printf("tile 4x3 m8n8k4, %d CTA/SM: %7.2f TFLOP/s\n", cps, flop / ms * 1e-9);
   }
+  for (int tpb : {32, 64, 128, 192}) {  // warps per SM: 1, 2, 4, 6
+    const int ctas = sms, iters = 2000;
+    const double ms = time_ms([&] { k_dmma_tile<4><<<ctas, tpb>>>(out, iters, 0.999999, 1e-9); });
+    const double flop = 512.0 * 4 * 2 * 12 * iters * (double)ctas * (tpb / 32);
+    std::printf("tile 4x3 m8n8k4, %d warps/SM: %7.2f TFLOP/s\n", tpb / 32, flop / ms * 1e-9);
+  }
   for (int cps : {1, 2, 3, 4}) {
     const int ctas = sms * cps, iters = 2000;
     const double ms = time_ms([&] { k_dmma_tile<2><<<ctas, 256>>>(out, iters, 0.999999, 1e-9); });
     const double flop = 512.0 * 4 * 2 * 6 * iters * (double)ctas * 8;
     std::printf("tile 2x3 m8n8k4, %d CTA/SM: %7.2f TFLOP/s\n", cps, flop / ms * 1e-9);
   }
+  run_mix<0>(out, sms);
+  run_mix<1>(out, sms);
+  run_mix<3>(out, sms);
+  run_mix<6>(out, sms);
+  run_mix<12>(out, sms);
+  run_mix<24>(out, sms);
   std::printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

@@ -105,7 +105,7 @@ def main():
         t2 = e2e("full TRG", d2, [("oracle", o2)])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.savez_compressed(os.path.join(ROOT, "gpurun_out", "e2e_tables.npz"), t1=t1, t2=t2)
-        print("DFMA peak TFLOP/s:", rt.dfma_peak_tflops(0, 0.5))
+        print("FP64 pipe peak TFLOP/s: DMMA loop", rt.dmma_peak_tflops(0, 0.5), " DFMA loop", rt.dfma_peak_tflops(0, 0.5))
 
 
 if __name__ == "__main__":
