@@ -26,7 +26,7 @@ namespace rtrg {
 // kernels_integrals.cu
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int groups, int identical,
-                     cudaStream_t st, Profiler *prof, const SideStream *side = nullptr);
+                     cudaStream_t st, Profiler *prof, const SideStream *side = nullptr, bool assemble = true);
 void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                         const int *mask, cudaStream_t st);
 int integrals_configure(const IntegralTabs &tb);
@@ -48,6 +48,9 @@ void launch_rhs(const Batch &S, const double *kgrid, const double *yv, double *d
                 const int *mask, cudaStream_t st);
 void launch_attempt_local(const Batch &S, const double *kgrid, const int *mask, cudaStream_t st);
 void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st);
+bool stage_post_applies(const Batch &S);
+void launch_stage_post(const IntegralTabs &tb, const Batch &S, const double *kgrid, const double *yv, int stage, int next,
+                       const int *mask, int groups, cudaStream_t st);
 void launch_final(const Batch &S, const int *mask, cudaStream_t st);
 void launch_ctrl_begin(const Batch &S, cudaStream_t st);
 void launch_ctrl_end(const Batch &S, int max_attempts, cudaStream_t st);
@@ -1240,19 +1243,30 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
   // a rank that leaves with an error wakes the ranks that would wait for it (loopback transport)
 #define XCH(call)                                                             \
   do {                                                                        \
-    if ((call) != 0) {                                                        \
+    RT_TIC(sharded ? h->prof : nullptr, PC_XCH, st);                          \
+    const int xrc_ = (call);                                                  \
+    RT_TOC(sharded ? h->prof : nullptr, st);                                  \
+    if (xrc_ != 0) {                                                          \
       h->xch->abort();                                                        \
       return fail(RTRG_ECUDA, "k-shard exchange: %s", xerr.c_str());          \
     }                                                                         \
   } while (0)
 
+  // small launches (one cosmology, k-sharded ranks): k_stage_post runs the assembly, the right-hand side
+  // and the combination of the next stage (or the error estimate) as one kernel
+  const bool fused = stage_post_applies(S) && !std::getenv("RTRG_NO_STAGE_FUSION");
   // --- dydt_in of the first step
   if (h->any_full) {
     std::vector<int> m(B);
     for (int b = 0; b < B; b++) m[b] = h->cos[b].c.sw_nl && !h->cos[b].c.sw_1l;
     CU(cudaMemcpyAsync(h->d_minit, m.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof, &h->side);
-    ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, h->d_minit, st));
+    if (fused) {
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof, &h->side, false);
+      ODE_LAUNCH(PC_STAGE, launch_stage_post(tb, S, h->d_kgrid, S.y, -1, 0, h->d_minit, grp_rhs(h), st));
+    } else {
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, h->d_minit, grp_rhs(h), 0, st, h->prof, &h->side);
+      ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, h->d_minit, st));
+    }
   }
 
   long long rounds = 0;
@@ -1274,7 +1288,16 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
       h->launches++;  // k_attempt_setup + k_attempt_local
     }
     // full Time-RG: the stages are separated by integral evaluations (and the k-shard exchange)
-    if (h->any_full) {
+    if (h->any_full && fused) {
+      ODE_LAUNCH(PC_COMBINE, launch_combine(S, 1, S.m_full_step, st));
+      for (int s = 1; s < RK_STAGES; s++) {
+        XCH(gather_lnP(S.ytmp));
+        h->launches += launch_integrals(tb, S, S.ytmp, (long long)N_U * nk, S.src, nullptr, S.m_full_step, grp_rhs(h), 0, st, h->prof, &h->side, false);
+        // sources, right-hand side of stage s, then ytmp of stage s + 1 (after the last stage: the
+        // 5th-order solution and the error norm)
+        ODE_LAUNCH(PC_STAGE, launch_stage_post(tb, S, h->d_kgrid, S.ytmp, s, s + 1, S.m_full_step, grp_rhs(h), st));
+      }
+    } else if (h->any_full) {
       for (int s = 1; s < RK_STAGES; s++) {
         ODE_LAUNCH(PC_COMBINE, launch_combine(S, s, S.m_full_step, st));
         XCH(gather_lnP(S.ytmp));
@@ -1287,7 +1310,10 @@ int rtrg_run(rtrg_handle *h, double *out, size_t out_len, double *hdr, double *h
     ODE_LAUNCH(PC_CTRL, launch_ctrl_end(S, h->cfg.max_attempts, st));
     ODE_LAUNCH(PC_ACCEPT, launch_accept(S, st));
     XCH(gather_lnP(S.y));  // keep ln P of the accepted state complete on every rank
-    if (h->any_full) {  // dydt_in of the next attempt
+    if (h->any_full && fused) {  // dydt_in of the next attempt
+      h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof, &h->side, false);
+      ODE_LAUNCH(PC_STAGE, launch_stage_post(tb, S, h->d_kgrid, S.y, -1, 0, S.m_full_acc, grp_rhs(h), st));
+    } else if (h->any_full) {
       h->launches += launch_integrals(tb, S, S.y, (long long)N_U * nk, S.src, nullptr, S.m_full_acc, grp_rhs(h), 0, st, h->prof, &h->side);
       ODE_LAUNCH(PC_RHS, launch_rhs(S, h->d_kgrid, S.y, S.kst, -1, S.m_full_acc, st));
     }
@@ -1546,7 +1572,7 @@ int rtrg_set_profiling(rtrg_handle *h, int on) {
 int rtrg_profile_categories(void) { return PC_NCAT; }
 const char *rtrg_profile_name(int cat) {
   static const char *names[PC_NCAT] = {"k_extrap", "k_bilinear", "k_jlo", "k_pz", "k_assemble", "k_rhs",
-                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_attempt_local", "k_prep_inputs", "k_beta_reduce",
+                                       "k_combine", "k_final", "k_ctrl", "k_accept", "k_output", "k_attempt_local", "k_stage_post", "k_xch", "k_prep_inputs", "k_beta_reduce",
                                        "k_growth_ode", "k_growth_tabs", "k_qag", "k_init_state"};
   return (cat >= 0 && cat < PC_NCAT) ? names[cat] : "";
 }

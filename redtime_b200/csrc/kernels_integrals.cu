@@ -2,28 +2,24 @@
 // extrapolated log-k power spectrum (replaces redTime.cc:740-1282).
 //
 //   k_extrap           Pab extrapolation + window (rt:181-232, 772-778)        HBM/latency bound
-//   k_bilinear(_packed) J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]   FP64 FMA pipe bound
+//   k_bilinear         J_n(k_i;A,B) = sum_{q1,q2} a(q1) b(q2) T_n[i-q1][i-q2]   FP64 pipe bound (DMMA)
 //   (compact_mask)     list of the cosmologies a launch is masked in for, built inside k_extrap
 //   k_jlo              J_0 at the low-k row nloMR (rt:1252,1267-1272)
 //   k_pz               P13-type log-convolutions PZ_n (rt:689-727)
 //   k_assemble         A_{acd,bef}, R^l_{abc}, P_T,jm, P_MR,n from the table of assembly_table.cc
 //
-// k_bilinear design (sm_100a): one CTA owns BIL_R = 8 consecutive output wavenumbers of one
-// kernel n and three slots, a slot being a (cosmology, beta-side spectrum) pair.  Because T_n is
-// circulant, rows i0..i0+7 read the same (nsup+7)^2 window of T_n shifted along the diagonal,
-// so each T element fetched from L2 feeds 8 rows x 3 slots = 24 DFMAs.  The spectra P q^2 of
-// the slots' cosmologies (reversed and zero padded, 8 KB each) are staged in shared memory by
-// TMA bulk copies (cp.async.bulk + mbarrier); every thread owns one alpha-side lag u, streams
-// its T column with coalesced 16-byte loads (two beta-side lags per element) that are
-// software-prefetched one 8-lag chunk ahead, and reads the beta-side window from shared memory
-// as broadcast 16-byte loads.  The (u) sums are reduced with warp shuffles (recursive halving).
-// Only the (kernel, spectrum) sets the requested output groups consume are computed; one set
-// is nk (2 nsup^2 + 6 nsup) FLOP, executed 2 nk (nsup+7)^2.
+// k_bilinear design (sm_100a): see the comment above the kernel -- per (kernel, row block of 8 rows,
+// slot) a dense matrix product T' x Hankel(spectrum) on the FP64 pipe as DMMA.8x8x4, T stored as 8 x 8
+// tiles in operand order and streamed from L2, the spectra staged in shared memory by TMA bulk
+// copies, followed by the alpha-side dot products.  Only the (kernel, spectrum) sets the requested
+// output groups consume are computed; one set is nk (2 nsup^2 + 6 nsup) FLOP useful, 2 nk NV^2
+// executed (NV = nsup + 7 rounded up to whole 8-lag tiles).
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
 #include "rtrg_device.h"
+#include "stage_device.h"
 
 namespace rtrg {
 
@@ -145,15 +141,19 @@ struct BilLaunch {
 // against 34.3 for a register-resident DFMA loop and 25.2 for the best DFMA form of this kernel
 // (tools/dmma_probe.cu, profiles/r02_bilinear_experiments.txt).
 //
-// A warp owns MT = 4 tiles of 8 alpha-side lags and NS slots: 4 NS accumulator tiles (8 x 8, two
+// A warp owns MT = 4 tiles of 8 alpha-side lags and NS = 3 slots: 12 accumulator tiles (8 x 8, two
 // doubles per lane).  Per chunk of 8 beta-side lags it issues 4 LDG.128 -- the T tiles are stored in
 // operand order, a warp reads 512 contiguous bytes per tile, prefetched one chunk ahead --, 2 NS
 // LDS.64 for the B fragments (lane (g, t): b_rev[v0 + 2 t - g + 7 + h]) and 8 NS DMMAs.  Every T
-// element fetched from L2 feeds 8 rows x NS slots FMAs.
+// element fetched from L2 feeds 8 rows x NS slots FMAs.  After the last chunk the lane's 2 x 3 NS
+// alpha-side products are formed as independent DFMA chains and reduced over the 8 lane groups by
+// recursive halving, then over the warps of the CTA through shared memory in a fixed pairwise order
+// (the scalar FP64 instructions of this part queue behind the DMMAs of the warps still in their main
+// loops, so the depth of its dependency chains is what counts: 7 instead of ~60 for the naive form).
 //
 // Work distribution.  The (row block, lag tile) pairs of ALL row blocks lie on one axis, item = rb NV +
-// lag, cut into CTAs of TPB consecutive items (TPB / 32 warps of 4 tiles).  A CTA touches up to
-// three row blocks (a warp at most two); that costs nothing inside the main loop because the B
+// lag, cut into CTAs of IPC = 32 NWARP consecutive items (NWARP warps of 4 tiles).  A CTA touches up
+// to three row blocks (a warp at most two); that costs nothing inside the main loop because the B
 // fragments do not depend on the row block, and the epilogue reduces the lags of each row block
 // separately.  The item axis is global (independent of k-sharding), so a sharded run adds the same
 // numbers in the same order as the unsharded one; per-slot arithmetic does not depend on which
@@ -170,7 +170,7 @@ template <int NWARP, int MT, int NS, int MINB>
 __global__ void __launch_bounds__(NWARP * 32, MINB)
     k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
                double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
-               const int *__restrict__ act, const int *__restrict__ nact, int dephase) {
+               const int *__restrict__ act, const int *__restrict__ nact) {
   constexpr int R = BIL_R, VC = 8;                  // rows per row block; lags per chunk
   constexpr int IPC = NWARP * MT * 8;               // items (alpha-side lags) per CTA
   constexpr int NSL = 3 * NS;                       // (slot, ab) sums per row
@@ -277,15 +277,6 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     for (int m = 0; m < MT; m++) tcur[m] = tnxt[m];
   }
 
-  if (dephase == -1) {  // experiment: main loop only
-    double sacc = 0;
-#pragma unroll
-    for (int m = 0; m < MT; m++)
-#pragma unroll
-      for (int q = 0; q < NS; q++) sacc += acc[m][q][0] + acc[m][q][1];
-    if (sacc == 123.456) Jpart[0] = sacc;
-    return;
-  }
   // alpha side, per slot: out[ab][r] = sum_u arev_ab[u - r + 7] * S[u][r], the sum running over the
   // lags of ONE row block.  Lane (g, t) holds S[tu_m + g][2 t] and S[tu_m + g][2 t + 1] of its tiles.
   // A warp holds tiles of one row block, or of two when it straddles a block boundary: side 0 = the
@@ -442,18 +433,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------- k_assemble
-__device__ __forceinline__ double kpow_i(double k, double kinv, int p) {
-  double r = 1.0;
-  if (p > 0)
-    for (int i = 0; i < p; i++) r *= k;
-  else
-    for (int i = 0; i < -p; i++) r *= kinv;
-  return r;
-}
-// ASM_ROWS rows per CTA: 16 for batches (the term table is read once per 16 rows), 4 when the
-// launch is small (one cosmology, k-sharded ranks), where more CTAs shorten the critical path.  The
-// arithmetic per row is the same.
-enum { ASM_NV = 190, ASM_MAXT = 768 };
+// (the pieces live in stage_device.h: k_stage_post runs the same code in front of the right-hand side)
 template <int ASM_ROWS>
 __global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
     k_assemble(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Jpart,
@@ -462,86 +442,16 @@ __global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
                int row0, int nrows, const int *__restrict__ mask, int groups) {
   const int e = blockIdx.y;
   if (mask && !mask[e]) return;
-  __shared__ double vals[ASM_NV][ASM_ROWS + 1];
-  // the assembly table (730 terms, 10 KB) once per CTA: the term loops then run out of shared memory
-  // instead of chains of dependent global loads
-  __shared__ double s_coef[ASM_MAXT];
-  __shared__ short s_src[ASM_MAXT], s_index[ASM_MAXT], s_kpow[ASM_MAXT];
-  __shared__ int s_start[N_SRC + 1];
-  for (int t = threadIdx.x; t < tb.n_terms; t += blockDim.x) {
-    s_coef[t] = tb.t_coef[t];
-    s_src[t] = tb.t_src[t];
-    s_index[t] = tb.t_index[t];
-    s_kpow[t] = tb.t_kpow[t];
-  }
-  for (int t = threadIdx.x; t <= N_SRC; t += blockDim.x) s_start[t] = tb.t_start[t];
+  __shared__ AsmShared<ASM_ROWS> sa;
   const int r0 = row0 + blockIdx.x * ASM_ROWS;
   const int rows = min(ASM_ROWS, row0 + nrows - r0);
-  const int has_jn0 = cosmo[e].sw_pr;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < ASM_NV * ASM_ROWS; idx += blockDim.x) {
-    const int v = idx / ASM_ROWS, rr = idx - v * ASM_ROWS;
-    if (rr >= rows) continue;
-    const int i = r0 + rr, ipad = tb.nshift + i;
-    double x = 0.0;
-    if (v < 63 || (v >= 126 && v < 189)) {
-      const int iJ = (v < 63) ? v : v - 126;
-      const int n = iJ / 9 + ((v < 63) ? 0 : 7), pair = iJ % 9;
-      if (v < 63 || has_jn0) {
-        // the parts k_bilinear wrote for this row block: per split of the beta-side lags, one per
-        // CTA along the item axis that holds some of the block's alpha-side lags
-        const int nch = tb.nchunk * tb.vsplit, rb = i / BIL_R;
-        const int np_rb = (rb * tb.NV + tb.NV - 1) / tb.tpb - (rb * tb.NV) / tb.tpb + 1;
-        RT_ASSERT(np_rb >= 1 && np_rb <= tb.nchunk && n < N_JKERN && pair < 9);
-        // added in (split, part) order; the loads of four parts are issued together -- one memory
-        // round trip per four parts instead of one per part (x + 0.0 is exact for the padding)
-        const double *pj = Jpart + ((((long long)e * N_JKERN + n) * nch) * 9 + pair) * tb.nk + i;
-        const long long pstride = 9LL * tb.nk;
-        const int nq = tb.vsplit * np_rb;
-        for (int q0 = 0; q0 < nq; q0 += 4) {
-          double t4[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int q = q0 + u, part = (q / np_rb) * tb.nchunk + q % np_rb;
-            t4[u] = q < nq ? pj[part * pstride] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) x += t4[u];
-        }
-        x *= tb.kfac[n * tb.nk + i];
-      }
-    } else if (v < 126) {
-      const int iJ = v - 63, n = iJ / 9, ab = (iJ % 9) / 3, cd = iJ % 3;
-      x = PZb[(((long long)e * N_ZKERN + n) * 3 + ab) * tb.nk + i];
-      if (cd) {  // rt:797-800
-        const double *P = P3 + (long long)e * 3 * tb.np;
-        x = x * P[cd * tb.np + ipad] / (P[ipad] + 1e-100);
-      }
-    } else {
-      x = Jlo[e];
-    }
-    vals[v][rr] = x;
-    if (raw) raw[((long long)e * ASM_NV + v) * tb.nk + i] = x;
-  }
+  asm_load_table(tb, sa);
+  asm_gather_vals(tb, cosmo[e].sw_pr, Jpart, PZb, P3, Jlo, raw, e, r0, rows, sa);
   __syncthreads();
-  for (int idx = tid; idx < N_SRC * ASM_ROWS; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < N_SRC * ASM_ROWS; idx += blockDim.x) {
     const int o = idx / ASM_ROWS, rr = idx - o * ASM_ROWS;
-    if (rr >= rows) continue;
-    // output groups: A rows 0-13, R 14-37, P_T,jm 38-46, P_MR,n 47-54; rows of groups that
-    // were not requested keep their old content (their inputs were not computed)
-    const int grp = o < 14 ? GRP_A : o < 38 ? GRP_R : o < 47 ? GRP_PT : GRP_PMR;
-    if (!(groups & grp)) continue;
-    const int i = r0 + rr;
-    const double k = tb.kgrid[i], kinv = 1.0 / k;
-    double acc = 0.0;
-    const int t1 = s_start[o + 1];
-    for (int t = s_start[o]; t < t1; t++) {
-      const int s = s_src[t];
-      const int v = (s == 3) ? 189 : s * 63 + s_index[t];
-      RT_ASSERT(v >= 0 && v < ASM_NV && t < tb.n_terms);
-      acc += s_coef[t] * kpow_i(k, kinv, s_kpow[t]) * vals[v][rr];
-    }
-    src[((long long)e * N_SRC + o) * tb.nk + i] = acc;
+    if (rr >= rows || !asm_wanted(o, groups)) continue;
+    src[((long long)e * N_SRC + o) * tb.nk + r0 + rr] = asm_source(tb, sa, o, rr, r0 + rr);
   }
 }
 
@@ -566,11 +476,7 @@ static int bil_variant_index() {
 int bilinear_tpb() { return kBilVariants[bil_variant_index()].ipc(); }
 size_t bilinear_smem_bytes(const IntegralTabs &tb) {
   const BilVariant v = kBilVariants[bil_variant_index()];
-  static const size_t extra = [] {
-    const char *e = std::getenv("RTRG_BIL_EXTRA_SMEM");
-    return e ? (size_t)std::atoi(e) : (size_t)0;
-  }();
-  return extra + (size_t)(3 * v.ns * tb.LP + v.nwarp * 2 * 3 * v.ns * BIL_R) * sizeof(double);
+  return (size_t)(3 * v.ns * tb.LP + v.nwarp * 2 * 3 * v.ns * BIL_R) * sizeof(double);
 }
 template <class F>
 static auto bil_dispatch(F &&f) {
@@ -595,7 +501,7 @@ static auto bil_dispatch(F &&f) {
 // event timing is on.
 int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, long long ystride,
                      double *src, double *raw, const int *mask, int groups, int identical,
-                     cudaStream_t st, Profiler *prof, const SideStream *side) {
+                     cudaStream_t st, Profiler *prof, const SideStream *side, bool assemble) {
   const int B = S.B, row0 = S.k_lo, nrows = S.k_hi - S.k_lo;
   int launches = 0;
   // work items: kernel n with the beta-side spectra the requested groups consume
@@ -617,6 +523,9 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     L.it[nitems++] = it;
     units += it.ncd;
   }
+  // heaviest items first (CTAs are dispatched in block order; a CTA's duration grows with the number of
+  // spectra of its item): the light ones fill the tail of a small launch
+  std::stable_sort(L.it, L.it + nitems, [](const BilItem &a, const BilItem &b) { return a.ncd > b.ncd; });
   L.replicate = identical ? 1 : 0;
   {
     dim3 g((tb.np + 127) / 128, B);
@@ -643,11 +552,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
       const int ipc = v.ipc(), ns = v.ns, tpb = v.nwarp * 32;
       const int c_lo = (rb_lo * tb.NV) / ipc, c_hi = (rb_hi * tb.NV - 1) / ipc;
       dim3 g((c_hi - c_lo + 1) * tb.vsplit, nitems, (B * maxncd + ns - 1) / ns);
-      static const int dephase = [] {
-        const char *e = std::getenv("RTRG_BIL_DEPHASE");
-        return e ? std::atoi(e) : 0;
-      }();
-      kern<<<g, tpb, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo, rb_hi, c_lo, S.act, S.nact, dephase);
+      kern<<<g, tpb, bilinear_smem_bytes(tb), st>>>(tb, S.cosmo, S.Prev, S.Jpart, L, rb_lo, rb_hi, c_lo, S.act, S.nact);
       return 0;
     });
     launches++;
@@ -676,7 +581,7 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     cudaEventRecord(side->join, st_side);
     cudaStreamWaitEvent(st, side->join, 0);
   }
-  {
+  if (assemble) {
     RT_TIC(prof, PC_ASSEMBLE, st);
     if ((long long)B * nrows <= 2048)
       k_assemble<4><<<dim3((nrows + 3) / 4, B), 768, 0, st>>>(tb, S.cosmo, S.Jpart, S.PZb, S.P3, S.Jlo, src, raw, row0,

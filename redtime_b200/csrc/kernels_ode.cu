@@ -16,120 +16,14 @@
 //   k_accept     y <- ynew for accepted cosmologies
 //   k_output     one nk x ncols table
 #include "rtrg_device.h"
+#include "stage_device.h"
 
 namespace rtrg {
-
-// linear quantities at grid wavenumber i through the pre-reduced rows (see kernels_linear.cu)
-__device__ __forceinline__ double ode_row_beta(const Batch &S, int b, int i, double a) {
-  const BetaTab t = beta_tab(S, S.cosmo[b]);
-  return beta_row(t, S.bred + (long long)b * S.n_zmax * S.nkk + i, a, S.nkk);
-}
-__device__ __forceinline__ bool ode_row_D_dD(const Batch &S, int b, int i, double z, double *D,
-                                             double *dD) {
-  const long long o = (long long)b * (S.n_lna + 1) * S.nk + i;
-  return growth_D_dD_row(S.lna, S.n_lna, S.Grow + o, S.dDrow + o, S.nk,
-                         S.D0row[(long long)b * S.nk + i], z, D, dD);
-}
-
-// ---------------------------------------------------------------------------- k_rhs
-// stage < 0: eta = t[b]; otherwise eta = t[b] + c_stage * h_try[b].
-// Everything that depends on the time only (background, interpolation weights in a of the beta
-// and growth tables, powers of e^eta) is evaluated once per block and shared: the 128 rows of a
-// block belong to one cosmology and are evaluated at the same eta.  The rows then read their 41
-// state values, 38 sources and a few table entries: HBM traffic 960 B per row.
-struct RhsShared {
-  double eta, eeta, A, om10_den, Om11, z, a, pre4;
-  RowX xb, xg;
-  int beta_zero, beta_bad, growth_ok;
-};
-// time-only part of one right-hand-side evaluation at eta (one thread per block)
-__device__ __forceinline__ void rhs_time_setup(const Batch &S, const Cosmo &c, double eta, RhsShared &sh) {
-  const double A = c.a_in * exp(eta);  // rt:1430
-  sh.eta = eta;
-  sh.eeta = exp(eta);
-  sh.A = A;
-  sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
-  sh.Om11 = 3.0 + bg_dlnH(c, A);
-  // Beta_P(A, k): 0 without massive neutrinos, abort in the reference for A > 1.001 (hdr:523-531)
-  sh.beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10);
-  sh.beta_bad = (!sh.beta_zero && A > 1.001);
-  if (!sh.beta_zero && !sh.beta_bad) sh.xb = tab_row_x_prepare(S.in + c.offA, c.n_z, A > 1.0 ? 1.0 : A);
-  // growth look-up of the 1-loop rescaling (rt:1316-1337)
-  sh.z = exp(-eta) * (1.0 + c.z_in) - 1;
-  sh.a = 1.0 / (sh.z + 1.0);
-  sh.growth_ok = !(sh.a > GROWTH_A_MAX || sh.a < GROWTH_A_MIN);
-  if (sh.growth_ok) sh.xg = tab_row_x_prepare(S.lna, S.n_lna + 1, log(sh.a));
-  sh.pre4 = exp(-4.0 * eta);
-}
-// The same, by all threads of a block together (k_rhs): the two table look-ups of rhs_time_setup are
-// binary searches -- chains of 4 + 7 dependent global loads, ~7 us of pure latency in front of every
-// right-hand side of a single cosmology.  Here every thread compares ONE node with the abscissa and
-// __syncthreads_count adds the votes: tab_find(x, n, xq) = #{1 <= i <= n-2 : x[i] < xq} for a sorted
-// table, one memory round trip.  Same index, same weights, same bits.
-__device__ __forceinline__ void rhs_time_setup_block(const Batch &S, const Cosmo &c, double eta, RhsShared &sh) {
-  const double A = c.a_in * exp(eta);
-  const bool beta_zero = (c.n_z == 0 || c.On / c.Om < 1e-10), beta_bad = (!beta_zero && A > 1.001);
-  const bool need_b = !beta_zero && !beta_bad;
-  const double xb = A > 1.0 ? 1.0 : A;
-  const double z = exp(-eta) * (1.0 + c.z_in) - 1, a = 1.0 / (z + 1.0);
-  const bool growth_ok = !(a > GROWTH_A_MAX || a < GROWTH_A_MIN);
-  const double xg = log(a);
-  const int nA = c.n_z, nG = S.n_lna + 1, nmax = nA > nG ? nA : nG;
-  const double *xa = S.in + c.offA;
-  int nb = 0, ng = 0;
-  for (int base = 0; base < nmax; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    nb += __syncthreads_count(need_b && i >= 1 && i <= nA - 2 && xa[i] < xb);
-    ng += __syncthreads_count(growth_ok && i >= 1 && i <= nG - 2 && S.lna[i] < xg);
-  }
-  if (threadIdx.x == 0) {
-    sh.eta = eta;
-    sh.eeta = exp(eta);
-    sh.A = A;
-    sh.om10_den = A * A * A * bg_H2(c, A);  // rt:1395-1401
-    sh.Om11 = 3.0 + bg_dlnH(c, A);
-    sh.beta_zero = beta_zero;
-    sh.beta_bad = beta_bad;
-    if (need_b) sh.xb = tab_row_x_prepare_at(xa, nA, xb, nb);
-    sh.pre4 = exp(-4.0 * eta);
-  }
-  if (threadIdx.x == 32 % blockDim.x) {
-    sh.z = z;
-    sh.a = a;
-    sh.growth_ok = growth_ok;
-    if (growth_ok) sh.xg = tab_row_x_prepare_at(S.lna, nG, xg, ng);
-  }
-  __syncthreads();
-}
-// row-dependent coefficients of that evaluation: Omega_10, and in 1-loop mode the rescaling of the
-// z1l cache, sources x (D/D_z1l)^4 e^{-4 eta} f^n (rt:1316-1337): *pre and f = *fz
-__device__ __forceinline__ void rhs_row_coeffs(const Batch &S, const Cosmo &c, int b, int i, const RhsShared &sh,
-                                               double *Om10, double *pre, double *fz) {
-  const int nk = S.nk;
-  double beta = 0.0;
-  if (sh.beta_bad) beta = NAN;
-  else if (!sh.beta_zero) beta = tab_row_x_apply(sh.xb, S.bred + (long long)b * S.n_zmax * S.nkk + i, S.nkk);
-  *Om10 = -1.5 * c.Om * (c.fcb + beta) / sh.om10_den;
-  *pre = 1.0;
-  *fz = 1.0;
-  if (c.sw_nl && c.sw_1l) {
-    double D = NAN, dD = NAN;
-    if (sh.growth_ok) {
-      const long long o = (long long)b * (S.n_lna + 1) * nk + i;
-      const double D0 = S.D0row[(long long)b * nk + i];
-      D = tab_row_x_apply(sh.xg, S.Grow + o, nk) * sh.a / D0;
-      dD = tab_row_x_apply(sh.xg, S.dDrow + o, nk) / D0;
-    }
-    *fz = dD / (D * (1.0 + sh.z));
-    const double rD = D / S.D_z1l[(long long)b * nk + i];
-    *pre = (rD * rD) * (rD * rD) * sh.pre4;
-  }
-}
 
 // SPLIT = false: one thread per row does the four pieces of the row one after the other (batches:
 // fewest redundant coefficient evaluations).  SPLIT = true: a thread per (row, piece), 32 rows per
 // block -- a quarter of the serial work per thread, for launches too small to fill the GPU (one
-// cosmology, k-sharded ranks).  Same arithmetic per component either way.
+// cosmology, k-sharded ranks).  Same arithmetic per component either way (rhs_row, stage_device.h).
 template <bool SPLIT>
 __global__ void __launch_bounds__(128)
     k_rhs(Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv,
@@ -143,56 +37,9 @@ __global__ void __launch_bounds__(128)
   const int piece = SPLIT ? (int)(threadIdx.x >> 5) : -1;
   const int i = S.k_lo + (SPLIT ? blockIdx.x * 32 + (threadIdx.x & 31) : blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= S.k_hi) return;
-  const double eeta = sh.eeta;
-  const double k = kgrid[i];
   const int one_loop = c.sw_nl && c.sw_1l;
-  const int evolve_Q = (S.print_Q || c.sw_pr);
-  double Om10, pre, fz;
-  rhs_row_coeffs(S, c, b, i, sh, &Om10, &pre, &fz);
-  const double Om11 = sh.Om11;
-  double fp[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
-  if (one_loop) {
-#pragma unroll
-    for (int p = 1; p < 5; p++) fp[p] = fp[p - 1] * fz;
-  }
   const double *s1 = (one_loop ? S.src_z1l : S.src) + (long long)b * N_SRC * nk + i;
-  const double *yb = yv + (long long)b * N_U * nk + i;
-  double *db = dyv + (long long)b * N_U * nk + i;
-
-  // The row is processed in four pieces (ln P + I, then the three multipoles of Q) so that at
-  // most 17 + 14 + 17 values are live at a time: 4x the occupancy of holding all 41 + 38 + 41.
-  if (!SPLIT || piece == 0) {
-    double y[N_UP + N_UI], dy[N_UP + N_UI], A14[N_UI];
-#pragma unroll
-    for (int j = 0; j < N_UP + N_UI; j++) y[j] = yb[(long long)j * nk];
-#pragma unroll
-    for (int j = 0; j < N_UI; j++)
-      A14[j] = !c.sw_nl ? 0.0 : one_loop ? pre * fp[a14_fpow(j)] * s1[(long long)j * nk] : s1[(long long)j * nk];
-    trg_rhs_PI(eeta, k, Om10, Om11, c.sw_nl, y, A14, dy);
-#pragma unroll
-    for (int j = 0; j < N_UP + N_UI; j++) db[(long long)j * nk] = dy[j];
-  }
-#pragma unroll
-  for (int l = 0; l < 3; l++) {
-    if (SPLIT && piece != l + 1) continue;
-    double Q[8], R[8], dQ[8];
-    const int j0 = N_UP + N_UI + 8 * l;
-    if (c.sw_nl && evolve_Q) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) Q[j] = yb[(long long)(j0 + j) * nk];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const double r = s1[(long long)(N_UI + 8 * l + j) * nk];
-        R[j] = one_loop ? pre * fp[r24_fpow(8 * l + j)] * r : r;
-      }
-      trg_rhs_Q(eeta, Om10, Om11, Q, R, dQ);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; j++) dQ[j] = 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) db[(long long)(j0 + j) * nk] = dQ[j];
-  }
+  rhs_row(S, c, b, i, piece, sh, kgrid[i], s1, nk, yv + (long long)b * N_U * nk + i, dyv + (long long)b * N_U * nk + i);
 }
 
 // ---------------------------------------------------------------------------- k_attempt_local
@@ -382,12 +229,7 @@ __global__ void k_combine(Batch S, int stage, const int *__restrict__ mask) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const long long o = (long long)b * n + idx, ks = (long long)S.B * n;
-  double acc = 0.0;
-  for (int j = 0; j < stage; j++) {
-    const double a = RKF45::a(stage, j);
-    if (a != 0.0) acc += a * S.kst[j * ks + o];
-  }
-  S.ytmp[o] = S.y[o] + S.h_try[b] * acc;
+  S.ytmp[o] = rk_combine(stage, S.y[o], S.h_try[b], S.kst + o, ks);
 }
 
 // ---------------------------------------------------------------------------- k_final
@@ -399,24 +241,13 @@ __global__ void __launch_bounds__(256) k_final(Batch S, const int *__restrict__ 
   double r = 0.0;
   if (idx < n) {
     const long long o = (long long)b * n + idx, ks = (long long)S.B * n;
-    const double h = S.h_try[b];
-    double acc = 0.0, err = 0.0;
-#pragma unroll
-    for (int j = 0; j < RK_STAGES; j++) {
-      const double kj = S.kst[j * ks + o];
-      if (RKF45::b(j) != 0.0) acc += RKF45::b(j) * kj;
-      if (RKF45::e(j) != 0.0) err += RKF45::e(j) * kj;
-    }
-    const double yn = S.y[o] + h * acc, ye = h * err;
+    double yn, ye;
+    const double rj = rk_final(S, S.y[o], S.h_try[b], S.kst + o, ks, &yn, &ye);
     S.ynew[o] = yn;
     S.yerr[o] = ye;
     // only rows owned by this rank contribute (k-sharding); all rows otherwise
     const int i = (int)(idx % S.nk);
-    if (i >= S.k_lo && i < S.k_hi) {
-      const double D0 = S.eps_rel * fabs(yn) + S.eps_abs;
-      r = fabs(ye) / fabs(D0);
-      if (!(r == r)) r = 0.0;  // GSL_MAX_DBL ignores NaN
-    }
+    if (i >= S.k_lo && i < S.k_hi) r = rj;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
@@ -426,6 +257,82 @@ __global__ void __launch_bounds__(256) k_final(Batch S, const int *__restrict__ 
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, s_r[w]);
     atomicMax(&S.rmax_bits[b], (unsigned long long)__double_as_longlong(r));
+  }
+}
+
+// ---------------------------------------------------------------------------- k_stage_post
+// Everything between the integrals of one Runge-Kutta stage and the exchange / integrals of the next,
+// for launches too small to fill the GPU (one cosmology, k-sharded ranks), where the kernel chain
+// k_assemble -> k_rhs -> k_combine (or k_final) is three launches of a few dependent memory round trips
+// each: per CTA of STG_ROWS rows of one cosmology
+//   1. the sources of the rows from the raw integrals (k_assemble's code),
+//   2. the right-hand side of stage `stage` into kst[stage] (k_rhs's code, sources read from shared memory),
+//   3. next in 1..5: ytmp of stage `next`;  next = 6: 5th-order solution, error estimate and error norm;
+//      next = 0: nothing (the dydt_in evaluation after an accepted step).
+// The same device functions in the same order as the separate kernels: same bits.
+enum { STG_ROWS = 4, STG_THREADS = 512 };
+__global__ void __launch_bounds__(STG_THREADS)
+    k_stage_post(IntegralTabs tb, Batch S, const double *__restrict__ kgrid, const double *__restrict__ yv, int stage,
+                 int next, const int *__restrict__ mask, int groups) {
+  const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
+  const Cosmo &c = S.cosmo[b];
+  const int nk = S.nk, tid = threadIdx.x;
+  __shared__ AsmShared<STG_ROWS> sa;
+  __shared__ double s_src[N_SRC][STG_ROWS + 1];
+  __shared__ RhsShared sh;
+  __shared__ double s_r[STG_THREADS / 32];
+  const int r0 = S.k_lo + blockIdx.x * STG_ROWS;
+  const int rows = min((int)STG_ROWS, S.k_hi - r0);
+  asm_load_table(tb, sa);
+  asm_gather_vals(tb, c.sw_pr, S.Jpart, S.PZb, S.P3, S.Jlo, nullptr, b, r0, rows, sa);
+  // (ends with a barrier: the raw values are in place as well)
+  rhs_time_setup_block(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
+  for (int idx = tid; idx < N_SRC * STG_ROWS; idx += STG_THREADS) {
+    const int o = idx / STG_ROWS, rr = idx - o * STG_ROWS;
+    if (rr >= rows || !asm_wanted(o, groups)) continue;  // (the right-hand side reads requested groups only)
+    const double v = asm_source(tb, sa, o, rr, r0 + rr);
+    s_src[o][rr] = v;
+    S.src[((long long)b * N_SRC + o) * nk + r0 + rr] = v;
+  }
+  __syncthreads();
+  const long long n = (long long)N_U * nk, ks = (long long)S.B * n;
+  double *dyv = S.kst + (size_t)(stage < 0 ? 0 : stage) * ks;
+  if (tid < 4 * STG_ROWS) {
+    const int piece = tid / STG_ROWS, rr = tid - piece * STG_ROWS;
+    if (rr < rows) {
+      const int i = r0 + rr;
+      const int one_loop = c.sw_nl && c.sw_1l;
+      const double *s1 = one_loop ? S.src_z1l + (long long)b * N_SRC * nk + i : &s_src[0][rr];
+      rhs_row(S, c, b, i, piece, sh, kgrid[i], s1, one_loop ? (long long)nk : (long long)(STG_ROWS + 1),
+              yv + (long long)b * n + i, dyv + (long long)b * n + i);
+    }
+  }
+  if (next == 0) return;
+  __syncthreads();  // (the derivatives just written are read back by other threads of the CTA)
+  double r = 0.0;
+  for (int idx = tid; idx < N_U * STG_ROWS; idx += STG_THREADS) {
+    const int j = idx / STG_ROWS, rr = idx - j * STG_ROWS;
+    if (rr >= rows) continue;
+    const long long o = (long long)b * n + (long long)j * nk + r0 + rr;
+    if (next < RK_STAGES) {
+      S.ytmp[o] = rk_combine(next, S.y[o], S.h_try[b], S.kst + o, ks);
+    } else {
+      double yn, ye;
+      r = fmax(r, rk_final(S, S.y[o], S.h_try[b], S.kst + o, ks, &yn, &ye));
+      S.ynew[o] = yn;
+      S.yerr[o] = ye;
+    }
+  }
+  if (next >= RK_STAGES) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((tid & 31) == 0) s_r[tid >> 5] = r;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < STG_THREADS / 32; w++) r = fmax(r, s_r[w]);
+      atomicMax(&S.rmax_bits[b], (unsigned long long)__double_as_longlong(r));
+    }
   }
 }
 
@@ -680,6 +587,13 @@ void launch_attempt_local(const Batch &S, const double *kgrid, const int *mask, 
   const int nrows = S.k_hi - S.k_lo;
   k_attempt_setup<<<(S.B * RK_STAGES + 127) / 128, 128, 0, st>>>(S, mask);
   k_attempt_local<<<dim3((nrows + ATT_ROWS - 1) / ATT_ROWS, S.B), 128, attempt_smem_bytes(), st>>>(S, kgrid, mask);
+}
+// small launches: the fused path (k_stage_post) replaces k_assemble + k_rhs + k_combine / k_final
+bool stage_post_applies(const Batch &S) { return (long long)S.B * (S.k_hi - S.k_lo) <= 2048; }
+void launch_stage_post(const IntegralTabs &tb, const Batch &S, const double *kgrid, const double *yv, int stage, int next,
+                       const int *mask, int groups, cudaStream_t st) {
+  const int nrows = S.k_hi - S.k_lo;
+  k_stage_post<<<dim3((nrows + STG_ROWS - 1) / STG_ROWS, S.B), STG_THREADS, 0, st>>>(tb, S, kgrid, yv, stage, next, mask, groups);
 }
 void launch_combine(const Batch &S, int stage, const int *mask, cudaStream_t st) {
   const long long n = (long long)N_U * S.nk;

@@ -7,7 +7,8 @@
 //   stage thread : rtrg_add_cosmologies  (host staging + H2D on the handle's copy stream)
 //                  rtrg_prepare          (device-side linear theory, sigma_8, 1-loop cache)
 //   run thread   : rtrg_run              (Time-RG evolution, output integrals, tables)
-//                  rtrg_fetch_outputs    (D2H into page-locked memory of the handle)
+//   fetch thread : rtrg_fetch_outputs    (D2H into page-locked memory of the handle; the next job's
+//                                         evolution is already running on the other handle)
 //
 // `depth` handles (2 = double buffering) live on the same device, each with its own streams and
 // work arena, so batch i+1 is staged, uploaded and initialised while batch i evolves: the host
@@ -41,11 +42,11 @@ struct rtrg_pipeline {
   std::vector<bool> slot_busy;
   std::mutex mu;
   std::condition_variable cv;
-  std::deque<Job *> to_stage, to_run;
+  std::deque<Job *> to_stage, to_run, to_fetch;
   std::vector<Job *> jobs;  // by ticket (never shrinks during the life of the pipeline; small)
   long long next_ticket = 0;
   bool stop = false;
-  std::thread stage_thread, run_thread;
+  std::thread stage_thread, run_thread, fetch_thread;
 };
 
 static void stage_loop(rtrg_pipeline *p) {
@@ -91,7 +92,32 @@ static void run_loop(rtrg_pipeline *p) {
       j->status.assign(j->list.size(), 0);
       rc = rtrg_run(h, nullptr, 0, nullptr, nullptr, j->status.data());
       if (rc == RTRG_EODE) rc = RTRG_OK;  // per-cosmology failures are reported through status[]
-      if (rc == RTRG_OK) rc = rtrg_fetch_outputs(h, &j->out, &j->out_len, &j->hdr, &j->hdr0);
+      if (rc != RTRG_OK) err = rtrg_last_error();
+    }
+    {
+      std::lock_guard<std::mutex> lk(p->mu);
+      j->rc = rc;
+      j->err = err;
+      p->to_fetch.push_back(j);
+    }
+    p->cv.notify_all();
+  }
+}
+
+static void fetch_loop(rtrg_pipeline *p) {
+  for (;;) {
+    Job *j = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(p->mu);
+      p->cv.wait(lk, [&] { return p->stop || !p->to_fetch.empty(); });
+      if (p->stop) return;
+      j = p->to_fetch.front();
+      p->to_fetch.pop_front();
+    }
+    int rc = j->rc;
+    std::string err = j->err;
+    if (rc == RTRG_OK) {
+      rc = rtrg_fetch_outputs(p->handles[j->slot], &j->out, &j->out_len, &j->hdr, &j->hdr0);
       if (rc != RTRG_OK) err = rtrg_last_error();
     }
     {
@@ -123,6 +149,7 @@ int rtrg_pipeline_create(const rtrg_config *cfg, int depth, rtrg_pipeline **out)
   p->slot_busy.assign(depth, false);
   p->stage_thread = std::thread(stage_loop, p);
   p->run_thread = std::thread(run_loop, p);
+  p->fetch_thread = std::thread(fetch_loop, p);
   *out = p;
   return RTRG_OK;
 }
@@ -201,6 +228,7 @@ int rtrg_pipeline_destroy(rtrg_pipeline *p) {
   p->cv.notify_all();
   if (p->stage_thread.joinable()) p->stage_thread.join();
   if (p->run_thread.joinable()) p->run_thread.join();
+  if (p->fetch_thread.joinable()) p->fetch_thread.join();
   for (Job *j : p->jobs) delete j;
   for (rtrg_handle *h : p->handles) rtrg_destroy(h);
   delete p;

@@ -144,7 +144,7 @@ struct Batch {
 // numbers).  Off by default: a null Profiler* costs nothing.
 enum ProfCat {
   PC_EXTRAP, PC_BILINEAR, PC_JLO, PC_PZ, PC_ASSEMBLE, PC_RHS, PC_COMBINE, PC_FINAL, PC_CTRL,
-  PC_ACCEPT, PC_OUTPUT, PC_ATTEMPT, PC_PREP_INPUTS, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
+  PC_ACCEPT, PC_OUTPUT, PC_ATTEMPT, PC_STAGE, PC_XCH, PC_PREP_INPUTS, PC_BETA_REDUCE, PC_GROWTH_ODE, PC_GROWTH_TABS, PC_QAG, PC_INIT_STATE,
   PC_NCAT
 };
 #ifdef __CUDACC__
