@@ -81,7 +81,7 @@ def test_table_cache_round_trip(tmp_path, example1_dir, stage_golden_1loop, monk
         res.append(h.integrals_raw(g["yp"][:3 * 128]))
         h.close()
     files = os.listdir(str(tmp_path / "cache"))
-    assert len(files) == 1 and files[0].startswith("T_v3_nk128_")
+    assert len(files) == 1 and files[0].startswith("T_v") and "_nk128_" in files[0]
     for a, b in zip(res[0][:3], res[1][:3]):
         assert np.array_equal(a, b)
     assert res[0][3] == res[1][3]

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Summarise ncu outputs into profiles/ (launch list CSV -> per-kernel table; .ncu-rep raw page
--> key metrics).  usage: ncu_summary.py launches <csv> <out.txt> <title> | kernel <ncu-rep> <out.txt> <title>"""
+-> key metrics).  usage: ncu_summary.py launches <csv> <out.txt> <title> | kernel <ncu-rep> <out.txt> <title>
+| metrics <ncu-rep> <out.csv> <title>   (metric,unit,value lines of the first kernel; bench.py parses dram__bytes_*)"""
 import collections
 import csv
 import subprocess
@@ -11,6 +12,8 @@ KEYS = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'lau
         'sm__warps_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
         'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
         'sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active',
@@ -62,5 +65,28 @@ def kernel(rep, out, title):
     print('\n'.join(o))
 
 
+CSV_KEYS = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum',
+            'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+            'l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+            'launch__block_size', 'launch__grid_size', 'launch__registers_per_thread', 'lts__t_sector_hit_rate.pct',
+            'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+            'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+            'sm__inst_executed_pipe_tensor.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+            'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max']
+
+
+def metrics(rep, out, title):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.split('\n')))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    o = ['# metric, unit, value: ' + title]
+    for k in CSV_KEYS:
+        if k in idx:
+            o.append('%s,%s,%s' % (k, units[idx[k]], r[idx[k]].replace(',', '')))
+    open(out, 'w').write('\n'.join(o) + '\n')
+    print('\n'.join(o))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel}[sys.argv[1]](*sys.argv[2:5])
+    {'launches': launches, 'kernel': kernel, 'metrics': metrics}[sys.argv[1]](*sys.argv[2:5])
