@@ -218,7 +218,7 @@ static void prof_collect(rtrg_handle *h) {
 // Bump TABLE_CACHE_VERSION whenever build_T (fastpt_tables.cc), the packing below (Tc layout,
 // BIL_R, the lag window) or this header changes: a file written by an older build is then rebuilt
 // instead of trusted.
-enum { TABLE_CACHE_VERSION = 4 };
+enum { TABLE_CACHE_VERSION = 5 };
 struct TableCacheHeader {
   char magic[8];
   int version, nk, np, nsup, n_tc, n_tlo, n_kfac, bil_r;
@@ -437,7 +437,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
 
   // --- circulant kernels, built in parallel on the host, packed into the compact layout
   const int UMIN = g.nshift - (np - 1), NU = nk + g.nsup - 1;
-  std::vector<double> Tc((size_t)N_JKERN * tb.NUp * tb.ldT, 0.0), kfac((size_t)N_JKERN * nk);
+  std::vector<double> Tc((size_t)(N_JKERN + N_TKERN) * tb.NUp * tb.ldT, 0.0), kfac((size_t)N_JKERN * nk);
   std::vector<double> Tlo((size_t)g.nsup * g.nsup);
   double kfac_lo = 0;
   const std::string cache = table_cache_path(g);
@@ -448,6 +448,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
         std::vector<double> T, kf;
         build_T(g, n, T, kf);
         double *dst = &Tc[(size_t)n * tb.NUp * tb.ldT];
+        double *dstT = (n >= TKERN_FIRST && n < TKERN_FIRST + N_TKERN) ? &Tc[(size_t)(N_JKERN + n - TKERN_FIRST) * tb.NUp * tb.ldT] : nullptr;
         for (int vv = 0; vv < NU; vv++) {
           const int v = ((vv + UMIN) % np + np) % np;
           for (int uu = 0; uu < NU; uu++) {
@@ -456,7 +457,9 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
             // DMMA.8x8x4: lane 4 g + t of a warp holds, as one 16-byte element, the beta-side lags
             // 2 t and 2 t + 1 of alpha-side lag g -- the A fragments of two consecutive MMAs
             const size_t tile = (size_t)(vv >> 3) * (tb.ldT / 8) + (uu >> 3);
-            dst[(tile * 32 + 4 * (uu & 7) + ((vv & 7) >> 1)) * 2 + (vv & 1)] = T[(size_t)u * np + v];
+            const size_t at = (tile * 32 + 4 * (uu & 7) + ((vv & 7) >> 1)) * 2 + (vv & 1);
+            dst[at] = T[(size_t)u * np + v];
+            if (dstT) dstT[at] = T[(size_t)v * np + u];  // the transposed copy (N_TKERN)
           }
         }
         for (int i = 0; i < nk; i++) kfac[(size_t)n * nk + i] = kf[g.nshift + i];
@@ -536,6 +539,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   }
   // which (kernel, beta-side spectrum) products each output group consumes
   std::memset(tb.need_cd, 0, sizeof tb.need_cd);
+  std::memset(tb.need_ab, 0, sizeof tb.need_ab);
   std::memset(tb.need_pz, 0, sizeof tb.need_pz);
   for (const AsmTerm &t : terms) {
     if (t.src == 1) {  // PZ: index = 9 n + 3 ab + cd, the convolution itself is PZ_n(P_ab)
@@ -546,6 +550,7 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
     const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
     const int n = t.index / 9 + (t.src == 2 ? 7 : 0), cd = t.index % 3;
     tb.need_cd[gi][n] |= (unsigned char)(1 << cd);
+    tb.need_ab[gi][n] |= (unsigned char)(1 << ((t.index % 9) / 3));
   }
 
   int rc = 0;

@@ -123,6 +123,8 @@ __global__ void k_extrap(IntegralTabs tb, const Cosmo *__restrict__ cosmo,
 // spectra are identical (1-loop cache at z1l, rt:1303-1305), one product serves all 9 pairs.
 struct BilItem {
   short n, ncd, cd[3];
+  short tn;    // table the matrix-vector product runs on: n, or the transposed copy of T_n
+  short swap;  // 1: transposed -- cd[] are alpha-side spectra, the dot products run over the beta side
 };
 struct BilLaunch {
   BilItem it[N_JKERN];
@@ -225,9 +227,9 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     const int rbc = min(max(rb_m[m], rb_lo), rb_hi - 1);  // idle tiles stream a valid column, are never added
     // tile (v''/8, u''/8) with u'' = 8 rbc + tu, v'' = 8 rbc + v
     Tp[m] = reinterpret_cast<const double2 *>(tb.Tc) +
-            (((size_t)n * (tb.NUp >> 3) + rbc) * NUT + rbc + (tu_m[m] >> 3)) * 32 + lane;
+            (((size_t)item.tn * (tb.NUp >> 3) + rbc) * NUT + rbc + (tu_m[m] >> 3)) * 32 + lane;
     RT_ASSERT(n >= 0 && n < N_JKERN && 8 * rbc + tu_m[m] + 8 <= tb.ldT && 8 * rbc + tb.NVp <= tb.NUp);
-    RT_ASSERT((((size_t)n * (tb.NUp >> 3) + rbc + (tb.NVp >> 3) - 1) * NUT + rbc + (tu_m[m] >> 3)) * 64 + 63 < (size_t)tb.n_Tc);
+    RT_ASSERT((((size_t)item.tn * (tb.NUp >> 3) + rbc + (tb.NVp >> 3) - 1) * NUT + rbc + (tu_m[m] >> 3)) * 64 + 63 < (size_t)tb.n_Tc);
   }
   const double *s_c[NS];
 #pragma unroll
@@ -362,7 +364,8 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
 #pragma unroll
       for (int pair = 0; pair < 9; pair++) dst[(long long)pair * tb.nk] = s;
     } else {
-      dst[(long long)(ab * 3 + s_cd[q]) * tb.nk] = s;
+      // (transposed items: the slot's spectrum is the alpha side of the pair)
+      dst[(long long)(item.swap ? s_cd[q] * 3 + ab : ab * 3 + s_cd[q]) * tb.nk] = s;
     }
   }
 }
@@ -515,7 +518,21 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
     if (!need) continue;
     if (identical) need = 1;
     BilItem it;
-    it.n = (short)n;
+    it.n = it.tn = (short)n;
+    it.swap = 0;
+    // J_n(ab, cd) = a_ab^T T_n b_cd: the matrix-vector product may run on either side.  Kernels with a
+    // transposed copy take the side with fewer spectra (the default output columns need (ab, cd) =
+    // (2, 1), (2, 2) of n = 7, 8, 9: one product T_n^T a_2 instead of two)
+    if (!identical && !(groups & GRP_RAW) && n >= TKERN_FIRST && n < TKERN_FIRST + N_TKERN) {
+      int need_a = 0;
+      for (int gi = 0; gi < 4; gi++)
+        if (groups & (1 << gi)) need_a |= tb.need_ab[gi][n];
+      if (__builtin_popcount(need_a) < __builtin_popcount(need)) {
+        need = need_a;
+        it.tn = (short)(N_JKERN + n - TKERN_FIRST);
+        it.swap = 1;
+      }
+    }
     it.ncd = 0;
     for (int c = 0; c < 3; c++)
       if (need & (1 << c)) it.cd[it.ncd++] = (short)c;

@@ -15,7 +15,7 @@
 //                      src    [B][55][nk]            A14, R24, PTjm9, PMRn8
 //   inputs             in     [sum over cosmologies of 3 nT + n_z + n_kb + 2 n_z n_kb]
 //                                                    raw CAMB columns, transformed in place
-//   weight tables      Tc     [14][NUp/8][ldT/8][32][2]  compact circulant kernels as 8 x 8 tiles in
+//   weight tables      Tc     [14+3][NUp/8][ldT/8][32][2]  compact circulant kernels (+ 3 transposes) as 8 x 8 tiles in
 //                                                    DMMA operand order (L2 resident)
 #pragma once
 #include "rtrg_math.h"
@@ -43,6 +43,11 @@ enum { RK_STAGES = 6, MAX_OUT = 64, N_SRC = 55, RMAX_HIST = 128 };
 enum { N_JKERN = 14, N_ZKERN = 7 };  // bilinear kernels (J + Jn0) and Z kernels
 #endif
 enum { BIL_R = 8 };      // output rows per row block of the bilinear kernel
+// Transposed copies of the asymmetric Jn0 kernels (alpha, beta, l) = (0, 2, l), n = 7, 8, 9: table
+// N_JKERN + n - 7 holds T_n^T, with which J_n(ab, cd) = a_ab^T T_n b_cd is evaluated as b_cd^T T_n^T a_ab,
+// i.e. with the matrix-vector product on the ab side.  The default output columns need the pairs
+// (ab, cd) = (2, 1), (2, 2) of these kernels: one product T_n^T a_2 instead of T_n b_1 and T_n b_2.
+enum { N_TKERN = 3, TKERN_FIRST = 7 };
 // output groups of one evaluation of the mode-coupling integrals
 enum { GRP_A = 1, GRP_R = 2, GRP_PT = 4, GRP_PMR = 8, GRP_ALL = 15, GRP_RAW = 16 };
 enum { RTRG_QAG_FAIL = 101, RTRG_ODE_FAIL = 102, RTRG_RANGE_FAIL = 103 };  // Cosmo::status
@@ -60,7 +65,7 @@ struct IntegralTabs {
   int vsplit;  // CTAs along the beta-side lag dimension (rtrg_config.v_split)
   double dlnk;     // grid spacing in ln k
   double kfac_lo;  // k-dependent prefactor of kernel 0 at the padded row nloMR
-  const double *Tc;    // [14][NUp/8][ldT/8][32][2]  tile (v''/8, u''/8), lane 4 (u''&7) + (v''&7)/2, half v''&1 = T_n[u][v]
+  const double *Tc;    // [14 + N_TKERN][NUp/8][ldT/8][32][2]  tile (v''/8, u''/8), lane 4 (u''&7) + (v''&7)/2, half v''&1 = T_n[u][v]
   const double *Tlo;   // [nsup][nsup]    kernel 0 at the low-k row nloMR (reversed indices)
   const double *kfac;  // [14][nk]
   const double *G;     // [7][2np-1]
@@ -73,6 +78,7 @@ struct IntegralTabs {
   const double *ex_dx;    // [np] lnk - lnk[nk-1] for the power-law extrapolation, else 0
   // beta-side spectra (bit c = P_{cd=c}) of kernel n consumed by output group g = A, R, PT, PMR
   unsigned char need_cd[4][N_JKERN];
+  unsigned char need_ab[4][N_JKERN];  // the same for the alpha side (bit a = P_{ab=a})
   unsigned int need_pz[4];  // bit 3 n + ab: the PZ_n(P_ab) log-convolutions an output group consumes
   // assembly table (sorted by output row)
   int n_terms;

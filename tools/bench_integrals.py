@@ -24,7 +24,7 @@ row, src, idx, kpw, cf = rt.assembly_terms()
 
 
 def sets(groups, ident):
-    need = {}
+    need, need_ab = {}, {}
     for r, s_, i in zip(row, src, idx):
         if s_ not in (0, 2):
             continue
@@ -35,8 +35,13 @@ def sets(groups, ident):
             if n in (0, 3, 6, 10, 11, 12, 13):  # symmetric kernels: pair (ab,cd) served by (min,max)
                 cd = max(ab, cd)
             need[n] = need.get(n, 0) | (1 << cd)
+            need_ab[n] = need_ab.get(n, 0) | (1 << ab)
     if groups & 16:
         need = {n: 7 for n in range(14)}
+    elif not ident:  # kernels 7-9 have transposed copies: the product runs on the side with fewer spectra
+        for n in (7, 8, 9):
+            if n in need and bin(need_ab.get(n, 7)).count("1") < bin(need[n]).count("1"):
+                need[n] = need_ab[n]
     return sum(1 if ident else bin(v).count("1") for v in need.values())
 
 
