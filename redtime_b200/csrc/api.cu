@@ -541,7 +541,13 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   std::memset(tb.need_cd, 0, sizeof tb.need_cd);
   std::memset(tb.need_ab, 0, sizeof tb.need_ab);
   std::memset(tb.need_pz, 0, sizeof tb.need_pz);
+  std::memset(tb.need_val, 0, sizeof tb.need_val);
   for (const AsmTerm &t : terms) {
+    {  // the raw value the term reads: J 0-62, PZ 63-125, Jn0 126-188, J_lo 189
+      const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
+      const int v = t.src == 3 ? 189 : t.src * 63 + t.index;
+      tb.need_val[gi][v >> 6] |= 1ULL << (v & 63);
+    }
     if (t.src == 1) {  // PZ: index = 9 n + 3 ab + cd, the convolution itself is PZ_n(P_ab)
       const int gi = t.row < 14 ? 0 : t.row < 38 ? 1 : t.row < 47 ? 2 : 3;
       tb.need_pz[gi] |= 1u << (3 * (t.index / 9) + (t.index % 9) / 3);

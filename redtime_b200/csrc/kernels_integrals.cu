@@ -125,6 +125,7 @@ struct BilItem {
   short n, ncd, cd[3];
   short tn;    // table the matrix-vector product runs on: n, or the transposed copy of T_n
   short swap;  // 1: transposed -- cd[] are alpha-side spectra, the dot products run over the beta side
+  short abmask;  // spectra of the dot-product side the requested outputs consume (bit a)
 };
 struct BilLaunch {
   BilItem it[N_JKERN];
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
   const int rbA = rb_m[0], rbB = rb_m[MT - 1];
   const int nside = (rbA == rbB) ? 1 : 2;
   if (lane == 0) s_wrb[warp][0] = rbA, s_wrb[warp][1] = (nside == 2) ? rbB : -1;
-  const int nab = L.replicate ? 1 : 3;
+  const int abmask = item.abmask;
   constexpr int NPV = (2 * NSL + 7) / 8 * 8;  // values per lane, padded to a multiple of 8
   for (int side = 0; side < nside; side++) {
     const int rbs = side ? rbB : rbA;
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
       for (int q = 0; q < NS; q++)
 #pragma unroll
         for (int ab = 0; ab < 3; ab++) {
+          if (!((abmask >> ab) & 1)) continue;  // (warp uniform)
           const double2 w = make_double2(ap[(q * 3 + ab) * LP], ap[(q * 3 + ab) * LP - 1]);
           pv[(q * 3 + ab) * 2] = fma(w.x, acc[m][q][0], pv[(q * 3 + ab) * 2]);
           pv[(q * 3 + ab) * 2 + 1] = fma(w.y, acc[m][q][1], pv[(q * 3 + ab) * 2 + 1]);
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     const int slot = x / R, r = x - slot * R, q = slot / 3, ab = slot - 3 * q;
     const int e = s_e[q];
     // Jn0 only feeds the RSD terms (rt:804): cosmologies without them keep their old entries
-    if (!s_ok[q] || ab >= nab || (n >= 7 && !cosmo[e].sw_pr)) continue;
+    if (!s_ok[q] || !((abmask >> ab) & 1) || (n >= 7 && !cosmo[e].sw_pr)) continue;
     // the warps' parts in a fixed pairwise order (x + 0.0 is exact for the warps of other blocks)
     double sw[NWARP];
 #pragma unroll
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(ASM_ROWS == 4 ? 768 : 256)
   const int r0 = row0 + blockIdx.x * ASM_ROWS;
   const int rows = min(ASM_ROWS, row0 + nrows - r0);
   asm_load_table(tb, sa);
-  asm_gather_vals(tb, cosmo[e].sw_pr, Jpart, PZb, P3, Jlo, raw, e, r0, rows, sa);
+  asm_gather_vals(tb, cosmo[e].sw_pr, Jpart, PZb, P3, Jlo, raw, e, r0, rows, groups, sa);
   __syncthreads();
   for (int idx = threadIdx.x; idx < N_SRC * ASM_ROWS; idx += blockDim.x) {
     const int o = idx / ASM_ROWS, rr = idx - o * ASM_ROWS;
@@ -533,6 +535,11 @@ int launch_integrals(const IntegralTabs &tb, const Batch &S, const double *y, lo
         it.swap = 1;
       }
     }
+    // the other side: only the dot products some requested output reads
+    int other = 0;
+    for (int gi = 0; gi < 4; gi++)
+      if (groups & (1 << gi)) other |= it.swap ? tb.need_cd[gi][n] : tb.need_ab[gi][n];
+    it.abmask = (short)((groups & GRP_RAW) ? 7 : identical ? 1 : other);
     it.ncd = 0;
     for (int c = 0; c < 3; c++)
       if (need & (1 << c)) it.cd[it.ncd++] = (short)c;

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(STG_THREADS)
   const int r0 = S.k_lo + blockIdx.x * STG_ROWS;
   const int rows = min((int)STG_ROWS, S.k_hi - r0);
   asm_load_table(tb, sa);
-  asm_gather_vals(tb, c.sw_pr, S.Jpart, S.PZb, S.P3, S.Jlo, nullptr, b, r0, rows, sa);
+  asm_gather_vals(tb, c.sw_pr, S.Jpart, S.PZb, S.P3, S.Jlo, nullptr, b, r0, rows, groups, sa);
   // (ends with a barrier: the raw values are in place as well)
   rhs_time_setup_block(S, c, (stage < 0) ? S.t[b] : S.t[b] + RKF45::c(stage) * S.h_try[b], sh);
   for (int idx = tid; idx < N_SRC * STG_ROWS; idx += STG_THREADS) {

@@ -80,6 +80,7 @@ struct IntegralTabs {
   unsigned char need_cd[4][N_JKERN];
   unsigned char need_ab[4][N_JKERN];  // the same for the alpha side (bit a = P_{ab=a})
   unsigned int need_pz[4];  // bit 3 n + ab: the PZ_n(P_ab) log-convolutions an output group consumes
+  unsigned long long need_val[4][3];  // bit v: raw value v (of 190, stage_device.h) is consumed by the group
   // assembly table (sorted by output row)
   int n_terms;
   const int *t_start;     // [56]

@@ -45,10 +45,21 @@ template <int ASM_ROWS>
 __device__ __forceinline__ void asm_gather_vals(const IntegralTabs &tb, int has_jn0, const double *__restrict__ Jpart,
                                                 const double *__restrict__ PZb, const double *__restrict__ P3,
                                                 const double *__restrict__ Jlo, double *__restrict__ raw, int e, int r0,
-                                                int rows, AsmShared<ASM_ROWS> &sa) {
+                                                int rows, int groups, AsmShared<ASM_ROWS> &sa) {
+  // only the values the requested groups consume are read (the others were not computed by this
+  // evaluation); with raw != nullptr all of them
+  unsigned long long want[3] = {0, 0, 0};
+  for (int gi = 0; gi < 4; gi++)
+    if (groups & (1 << gi))
+      for (int w = 0; w < 3; w++) want[w] |= tb.need_val[gi][w];
+  if (raw || (groups & GRP_RAW)) want[0] = want[1] = want[2] = ~0ULL;
   for (int idx = threadIdx.x; idx < ASM_NV * ASM_ROWS; idx += blockDim.x) {
     const int v = idx / ASM_ROWS, rr = idx - v * ASM_ROWS;
     if (rr >= rows) continue;
+    if (!((want[v >> 6] >> (v & 63)) & 1ULL)) {
+      sa.vals[v][rr] = 0.0;
+      continue;
+    }
     const int i = r0 + rr, ipad = tb.nshift + i;
     double x = 0.0;
     if (v < 63 || (v >= 126 && v < 189)) {
