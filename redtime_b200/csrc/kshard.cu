@@ -40,90 +40,90 @@ static inline int xch_blocks(const GatherPlan &p) { return p.nseg < 1 ? 1 : (p.n
 
 // ------------------------------------------------------------------------ P2P mailboxes
 // Mailbox of one rank (in ITS device memory, mapped into every peer by cudaIpc):
-//   flag [2][G]       sequence number of the last exchange source rank g completed into slot p
-//   data [2][G][cap]  8-byte words: the packed block of source rank g
+//   data [2][G][cap]  8-byte words written by source rank g
+// Every 8-byte word on the wire is self-validating (the "LL" scheme of NCCL's low-latency protocol):
+// 32 bits of payload + a 32-bit tag derived from the exchange number, written by ONE store, so the
+// receiver simply polls the word until the tag matches -- no fence, no separate flag, no second trip
+// over NVLink: the latency of an exchange is one remote store plus the poll.  A double travels as two
+// such words (one 16-byte vector store; each half is validated on its own).
 // Two slots alternate with the parity of the exchange number: a rank can run at most one exchange
-// ahead of the slowest peer (it needs everybody's flag of exchange n to start n + 1), so the slot
-// it overwrites in exchange n + 1 holds data of exchange n - 1, which every peer has consumed.
+// ahead of the slowest peer (it needs everybody's words of exchange n to start n + 1), so the slot
+// it overwrites in exchange n + 1 holds words of exchange n - 1, which every peer has consumed, and
+// their tags differ from the ones polled for.
 struct P2pDev {
   int rank, nranks;
-  long long cap;                       // words per (slot, source rank)
+  long long cap;                       // words per (slot, source rank); payload capacity cap / 2
   char *const *peer;                   // [G] device table: base of every rank's mailbox (own included)
   unsigned long long *seq;             // exchanges completed by this rank
   int *err;                            // set when a wait gave up
-  __device__ unsigned long long *flag(int owner, int slot, int src) const {
-    return reinterpret_cast<unsigned long long *>(peer[owner]) + slot * nranks + src;
-  }
-  __device__ unsigned long long *data(int owner, int slot, int src) const {
-    return reinterpret_cast<unsigned long long *>(peer[owner]) + 2 * nranks + ((long long)slot * nranks + src) * cap;
+  __device__ ulonglong2 *data(int owner, int slot, int src) const {
+    return reinterpret_cast<ulonglong2 *>(reinterpret_cast<unsigned long long *>(peer[owner]) + 2 * nranks +
+                                          ((long long)slot * nranks + src) * cap);
   }
 };
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_ll(ulonglong2 *p, unsigned long long v, unsigned long long tag) {
+  const unsigned long long w0 = (v & 0xffffffffULL) | (tag << 32), w1 = (v >> 32) | (tag << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+// poll until both halves carry the tag (bounded: ~10 s of SM clock -- ranks may enter rtrg_run seconds
+// apart, e.g. after building weight tables; a peer that never comes sets err)
+__device__ __forceinline__ unsigned long long ld_ll(const ulonglong2 *p, unsigned long long tag, int *err) {
+  unsigned long long w0, w1;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+    if (clock64() - t0 > 20000000000LL) {
+      atomicExch(err, 1);
+      return 0ULL;
+    }
+  }
+  return (w0 & 0xffffffffULL) | (w1 << 32);
 }
-// ONE kernel per exchange: pack this rank's words, store them into every rank's mailbox over
-// NVLink, publish the sequence flag, wait for the peers' flags, unpack (MODE 0: scatter the ln P
-// rows into `base`) or reduce (MODE 1: vals[i] = max over ranks).  One CTA: the payload is
-// 3 nk / G doubles per cosmology.
+
+// ONE kernel per exchange: store this rank's words into every peer's mailbox over NVLink, then
+// collect the peers' words from the own mailbox: MODE 0 scatters the ln P rows into `base`, MODE 1
+// reduces vals[i] = max over ranks.  One CTA: the payload is 3 nk / G doubles per cosmology.
 template <int MODE>
 __global__ void __launch_bounds__(512) k_xch_p2p(P2pDev d, GatherPlan plan, double *__restrict__ base,
                                                  unsigned long long *__restrict__ vals, int n) {
   const int tid = threadIdx.x, G = d.nranks, me = d.rank;
   if (*d.err) return;  // a peer is gone: do not wait for it again
   const unsigned long long s = *d.seq, want = s + 1;
+  const unsigned long long tag = (want & 0x7fffffffULL) | 0x80000000ULL;  // never 0 (the mailbox starts zeroed)
   const int slot = (int)(s & 1ULL);
-  // 1. pack + remote stores
+  // 1. remote stores
   if (MODE == 0) {
     for (int sg = 0; sg < plan.nseg; sg++) {
       const int len = plan.len[sg];
       const long long pre = plan.prefix[sg];
       const unsigned long long *src =
           reinterpret_cast<const unsigned long long *>(base + plan.off[sg] + (long long)me * len);
+      RT_ASSERT(2 * (pre + len) <= d.cap);
       for (int i = tid; i < len; i += blockDim.x) {
         const unsigned long long v = src[i];
         for (int r = 0; r < G; r++)
-          if (r != me) d.data(r, slot, me)[pre + i] = v;
+          if (r != me) st_ll(d.data(r, slot, me) + pre + i, v, tag);
       }
     }
   } else {
+    RT_ASSERT(2LL * n <= d.cap);
     for (int i = tid; i < n; i += blockDim.x) {
       const unsigned long long v = vals[i];
       for (int r = 0; r < G; r++)
-        if (r != me) d.data(r, slot, me)[i] = v;
+        if (r != me) st_ll(d.data(r, slot, me) + i, v, tag);
     }
   }
-  // 2. publish: every thread's stores are ordered before the flag by fence + barrier + release
-  __threadfence_system();
-  __syncthreads();
-  if (tid < G && tid != me) st_release_sys(d.flag(tid, slot, me), want);
-  // 3. wait for every peer's flag in my own mailbox (bounded: ~10 s of SM clock -- ranks may enter
-  //    rtrg_run seconds apart, e.g. after building weight tables; a peer that never comes sets err)
-  if (tid < G && tid != me) {
-    const unsigned long long *f = d.flag(me, slot, tid);
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < want) {
-      if (clock64() - t0 > 20000000000LL) {
-        atomicExch(d.err, 1);
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  // 4. unpack / reduce from my mailbox (L2 reads: the words were written by the peers)
+  // 2. collect from my mailbox (the words are written by the peers: volatile loads, straight from L2)
   if (MODE == 0) {
     for (int sg = 0; sg < plan.nseg; sg++) {
       const int len = plan.len[sg];
       const long long pre = plan.prefix[sg];
       for (int r = 0; r < G; r++) {
         if (r == me) continue;
-        const unsigned long long *src = d.data(me, slot, r) + pre;
+        const ulonglong2 *src = d.data(me, slot, r) + pre;
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(base + plan.off[sg] + (long long)r * len);
-        for (int i = tid; i < len; i += blockDim.x) dst[i] = __ldcg(src + i);
+        for (int i = tid; i < len; i += blockDim.x) dst[i] = ld_ll(src + i, tag, d.err);
       }
     }
   } else {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(512) k_xch_p2p(P2pDev d, GatherPlan plan, doub
       unsigned long long m = vals[i];
       for (int r = 0; r < G; r++) {
         if (r == me) continue;
-        const unsigned long long v = __ldcg(d.data(me, slot, r) + i);
+        const unsigned long long v = ld_ll(d.data(me, slot, r) + i, tag, d.err);
         m = v > m ? v : m;
       }
       vals[i] = m;
@@ -210,7 +210,7 @@ class NcclExchange : public Exchange {
   bool capturable() const override { return true; }
   bool device_side() const override { return p2p_; }
   const char *name() const override {
-    return p2p_ ? "P2P mailboxes over NVLink (one kernel per exchange: stores into peer memory + sequence flags; "
+    return p2p_ ? "P2P mailboxes over NVLink (one kernel per exchange: self-validating 8-byte words stored into peer memory, polled by the receiver; "
                   "NCCL for bootstrap and the final bulk gather)"
                 : "NCCL: pack -> one ncclAllGather -> unpack per exchange, ncclAllReduce(max) per attempt";
   }
@@ -291,7 +291,7 @@ class NcclExchange : public Exchange {
     return 0;
   }
   int gather(double *base, const GatherPlan &plan, bool small, cudaStream_t st, std::string *err) override {
-    if (p2p_ && small && plan.total <= cap_) {
+    if (p2p_ && small && 2 * plan.total <= cap_) {
       k_xch_p2p<0><<<1, 512, 0, st>>>(dev(), plan, base, nullptr, 0);
       return 0;
     }
@@ -306,7 +306,7 @@ class NcclExchange : public Exchange {
     return 0;
   }
   int allreduce_max_u64(unsigned long long *dev_vals, size_t n, cudaStream_t st, std::string *err) override {
-    if (p2p_ && (long long)n <= cap_) {
+    if (p2p_ && 2 * (long long)n <= cap_) {
       k_xch_p2p<1><<<1, 512, 0, st>>>(dev(), GatherPlan(), nullptr, dev_vals, (int)n);
       return 0;
     }
