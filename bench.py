@@ -467,6 +467,9 @@ def measure_batch(a, comm, rank, world, local_rank, B, nk, mode, steps, warm, wa
             tables, hdr, hdr0, status = pipe.wait(tickets[i], raise_on_failure=False)
             check.append(float(tables[B // 2][-1, nk // 2, 7]))   # the host reads the step's result
             n_failed = max(n_failed, int(np.count_nonzero(status)))
+            if os.environ.get("RTRG_PIPE_TIMES") and rank == 0:
+                print("pipe job %d: stage %.1f-%.1f run %.1f-%.1f fetch %.1f-%.1f ms" %
+                      ((i,) + tuple(1e3 * x for x in pipe.times(tickets[i]))), file=sys.stderr)
             if i == steps - 1:
                 d2h = sum(t.nbytes for t in tables) + hdr.nbytes + hdr0.nbytes
                 if keep_tables:

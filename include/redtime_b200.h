@@ -155,6 +155,10 @@ int rtrg_pipeline_wait(rtrg_pipeline *p, long long ticket, const double **out, s
 /* columns of cosmology i of a finished batch (rtrg_num_columns) */
 int rtrg_pipeline_columns(rtrg_pipeline *p, long long ticket, int icosmo);
 int rtrg_pipeline_release(rtrg_pipeline *p, long long ticket);
+/* Diagnostics: host-clock seconds since rtrg_pipeline_create at which the job's stage (staging,
+ * H2D, initialisation), run (evolution) and fetch (D2H) phases began and ended:
+ * t = {stage0, stage1, run0, run1, fetch0, fetch1}.  Valid once rtrg_pipeline_wait() has returned. */
+int rtrg_pipeline_times(rtrg_pipeline *p, long long ticket, double t[6]);
 int rtrg_pipeline_destroy(rtrg_pipeline *p);
 
 /* ---- one high-resolution cosmology sharded over its k-rows ---------------

@@ -276,6 +276,7 @@ class Pipeline:
                                            C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_ip)]
         lib.rtrg_pipeline_columns.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
         lib.rtrg_pipeline_release.argtypes = [C.c_void_p, C.c_longlong]
+        lib.rtrg_pipeline_times.argtypes = [C.c_void_p, C.c_longlong, _dp]
         lib.rtrg_pipeline_destroy.argtypes = [C.c_void_p]
         self.p = C.c_void_p()
         _check(lib.rtrg_pipeline_create(C.byref(self.cfg), int(depth), C.byref(self.p)))
@@ -309,6 +310,12 @@ class Pipeline:
             tables.append(out[o:o + sz].reshape(packed.n_out[i], self.nk, ncols))
             o += sz
         return tables, hdr, hdr0, status
+
+    def times(self, ticket):
+        """(stage0, stage1, run0, run1, fetch0, fetch1) of a finished job, seconds since creation."""
+        t = (C.c_double * 6)()
+        _check(self.lib.rtrg_pipeline_times(self.p, ticket, t))
+        return tuple(t)
 
     def release(self, ticket):
         _check(self.lib.rtrg_pipeline_release(self.p, ticket))

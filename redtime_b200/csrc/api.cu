@@ -32,6 +32,9 @@ void launch_extrap_only(const IntegralTabs &tb, const Batch &S, const double *y,
 int integrals_configure(const IntegralTabs &tb);
 size_t bilinear_smem_bytes(const IntegralTabs &tb);
 int bilinear_tpb();
+// host_stage.cc
+void beta_row_cubic(const double *tn, const double *tc, size_t n, double fn, const double *x, double xq, double *row1);
+void beta_row_linear(const double *tn, const double *tc, size_t n, double fn, double x0, double x1, double xq, double *row1);
 // kernels_linear.cu
 int linear_upload_constants();
 int launch_linear_init(const Batch &S, const double *kgrid, cudaStream_t st, Profiler *prof);
@@ -770,12 +773,11 @@ static void stage_cosmology(const rtrg_handle *h, const rtrg_cosmology *in, cons
     auto beta = [&](size_t j, size_t i) { return fn * tn[j * nkb + i] / tc[j * nkb + i]; };
     double *row1 = s, *bred = row1 + nkb;
     const int X = (int)nz, nx = tab_find(a, X, 1.0);
-    if (nx > 0 && nx < X - 2) {
-      for (size_t i = 0; i < nkb; i++)
-        row1[i] = cub4(a + nx - 1, beta(nx - 1, i), beta(nx, i), beta(nx + 1, i), beta(nx + 2, i), 1.0);
-    } else {
-      for (size_t i = 0; i < nkb; i++) row1[i] = lin2(a[nx], a[nx + 1], beta(nx, i), beta(nx + 1, i), 1.0);
-    }
+    // (vectorised, same bits as cub4 / lin2 per column: host_stage.cc)
+    if (nx > 0 && nx < X - 2)
+      beta_row_cubic(tn + (size_t)(nx - 1) * nkb, tc + (size_t)(nx - 1) * nkb, nkb, fn, a + nx - 1, 1.0, row1);
+    else
+      beta_row_linear(tn + (size_t)nx * nkb, tc + (size_t)nx * nkb, nkb, fn, a[nx], a[nx + 1], 1.0, row1);
     const size_t nkk = h->slot_k.size();
     for (size_t kk = 0; kk < nkk; kk++) {
       const Stencil st = tab_stencil_y(kb, (int)nkb, h->slot_k[kk]);

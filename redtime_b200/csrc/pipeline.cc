@@ -14,6 +14,7 @@
 // work arena, so batch i+1 is staged, uploaded and initialised while batch i evolves: the host
 // work and the PCIe transfers disappear behind the GPU time of the previous batch.  Every result
 // is bit-identical to the serial add/prepare/run sequence -- the handles are independent.
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -34,6 +35,7 @@ struct Job {
   const double *out = nullptr, *hdr = nullptr, *hdr0 = nullptr;
   size_t out_len = 0;
   std::vector<int> status;
+  double t[6] = {0, 0, 0, 0, 0, 0};  // seconds since pipeline creation: stage, run, fetch begin / end
 };
 }  // namespace
 
@@ -47,6 +49,8 @@ struct rtrg_pipeline {
   long long next_ticket = 0;
   bool stop = false;
   std::thread stage_thread, run_thread, fetch_thread;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double now() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 static void stage_loop(rtrg_pipeline *p) {
@@ -61,9 +65,11 @@ static void stage_loop(rtrg_pipeline *p) {
       p->slot_busy[j->slot] = true;
     }
     rtrg_handle *h = p->handles[j->slot];
+    j->t[0] = p->now();
     int rc = rtrg_clear_cosmologies(h);
     if (rc == RTRG_OK) rc = rtrg_add_cosmologies(h, (int)j->list.size(), j->list.data());
     if (rc == RTRG_OK) rc = rtrg_prepare(h);
+    j->t[1] = p->now();
     {
       std::lock_guard<std::mutex> lk(p->mu);
       j->rc = rc;
@@ -87,6 +93,7 @@ static void run_loop(rtrg_pipeline *p) {
     }
     int rc = j->rc;
     std::string err = j->err;
+    j->t[2] = p->now();
     if (rc == RTRG_OK) {
       rtrg_handle *h = p->handles[j->slot];
       j->status.assign(j->list.size(), 0);
@@ -94,6 +101,7 @@ static void run_loop(rtrg_pipeline *p) {
       if (rc == RTRG_EODE) rc = RTRG_OK;  // per-cosmology failures are reported through status[]
       if (rc != RTRG_OK) err = rtrg_last_error();
     }
+    j->t[3] = p->now();
     {
       std::lock_guard<std::mutex> lk(p->mu);
       j->rc = rc;
@@ -116,10 +124,12 @@ static void fetch_loop(rtrg_pipeline *p) {
     }
     int rc = j->rc;
     std::string err = j->err;
+    j->t[4] = p->now();
     if (rc == RTRG_OK) {
       rc = rtrg_fetch_outputs(p->handles[j->slot], &j->out, &j->out_len, &j->hdr, &j->hdr0);
       if (rc != RTRG_OK) err = rtrg_last_error();
     }
+    j->t[5] = p->now();
     {
       std::lock_guard<std::mutex> lk(p->mu);
       j->rc = rc;
@@ -193,6 +203,14 @@ int rtrg_pipeline_columns(rtrg_pipeline *p, long long ticket, int icosmo) {
       p->jobs[ticket]->released)
     return RTRG_EINVAL;
   return rtrg_num_columns(p->handles[p->jobs[ticket]->slot], icosmo);
+}
+
+int rtrg_pipeline_times(rtrg_pipeline *p, long long ticket, double t[6]) {
+  if (!p || !t) return RTRG_EINVAL;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (ticket < 0 || ticket >= (long long)p->jobs.size() || !p->jobs[ticket] || !p->jobs[ticket]->done) return RTRG_EINVAL;
+  for (int i = 0; i < 6; i++) t[i] = p->jobs[ticket]->t[i];
+  return RTRG_OK;
 }
 
 int rtrg_pipeline_release(rtrg_pipeline *p, long long ticket) {
