@@ -146,6 +146,10 @@ struct rtrg_handle {
   rtrg_config cfg;
   GridSpec grid;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // device-side initialisation (rtrg_device_init) runs on a stream of the highest priority: its
+  // latency-bound kernels (growth ODE, QAG) get the SM slots another handle's k_bilinear launch frees,
+  // i.e. they run beside it instead of after it (pipelines of several handles on one GPU)
+  cudaStream_t init_stream = nullptr;
   IntegralTabs tb;
   std::vector<void *> table_allocs, batch_allocs;
   StagingArena stage;
@@ -385,6 +389,11 @@ int rtrg_create(const rtrg_config *cfg, rtrg_handle **out) {
   std::memset(&h->tb, 0, sizeof h->tb);
   {
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+      int least = 0, greatest = 0;
+      cudaDeviceGetStreamPriorityRange(&least, &greatest);
+      e = cudaStreamCreateWithPriority(&h->init_stream, cudaStreamNonBlocking, greatest);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side.stream, cudaStreamNonBlocking);
@@ -604,6 +613,7 @@ int rtrg_destroy(rtrg_handle *h) {
   if (h->side.stream) cudaStreamDestroy(h->side.stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->init_stream) cudaStreamDestroy(h->init_stream);
   delete h;
   return RTRG_OK;
 }
@@ -647,6 +657,14 @@ static int host_threads(int cap) {
     if (ws > 1) n = n / ws;
   }
   return std::max(1, std::min(n, cap));
+}
+
+// Stream of the device work of rtrg_prepare / rtrg_device_init: the handle's high-priority stream
+// (see rtrg_handle::init_stream) unless the caller supplied a stream.  Both functions end with a
+// synchronisation, so what follows on h->stream is ordered by the host.
+static cudaStream_t prep_stream(const rtrg_handle *h) {
+  static const bool init_prio = !std::getenv("RTRG_NO_INIT_PRIORITY");
+  return (init_prio && h->stream == h->own_stream && h->init_stream) ? h->init_stream : h->stream;
 }
 
 static int check_cosmology(const rtrg_cosmology *in) {
@@ -1133,7 +1151,7 @@ int rtrg_prepare(rtrg_handle *h) {
   S.lna = d_lna;
   S.lnkg = d_lnkg;
 
-  cudaStream_t st = h->stream;
+  cudaStream_t st = prep_stream(h);
   // zero everything once (the Prev padding, the Q/I state rows ... rely on it)
   CU(cudaMemsetAsync(h->work.base, 0, h->work.used, st));
   // --- input pool: rtrg_add_cosmologies already sent the staged tables on the copy stream.  A
@@ -1190,7 +1208,8 @@ int rtrg_device_init(rtrg_handle *h) {
   const IntegralTabs &tb = h->tb;
   const int B = S.B, nk = S.nk;
   const size_t NE = (size_t)B * N_U * nk;
-  cudaStream_t st = h->stream;
+  // (everything issued before is complete: rtrg_prepare synchronised; this function synchronises at its end)
+  cudaStream_t st = prep_stream(h);
   CU(cudaMemsetAsync(S.matvecs, 0, B * sizeof(long long), st));
   CU(cudaMemsetAsync(S.matvecs_v, 0, S.NO * sizeof(long long), st));
   h->launches += launch_linear_init(S, h->d_kgrid, st, h->prof);
