@@ -193,3 +193,32 @@ def test_number_format_is_printf_20_12g():
     got = buf.value.decode()
     for i, x in enumerate(v):
         assert got[20 * i:20 * i + 20] == "%20.12g" % x, (x, got[20 * i:20 * i + 20], "%20.12g" % x)
+
+
+def test_vectorised_beta_row_staging_is_bit_identical(tmp_path):
+    """rtrg_add_cosmologies (reduce_beta = 1) forms beta(a = 1, k_b) with host_stage.cc: packed divisions,
+    interpolation weights formed once.  Same bits as cub4 / lin2 (rtrg_math.h) column by column, on the
+    example's own table size and on ragged lengths (vector remainders)."""
+    import ctypes as C
+    import subprocess
+    from conftest import ROOT
+    so = str(tmp_path / "libsh.so")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+                    os.path.join(ROOT, "tests", "harness", "stage_harness.cc"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.sh_row_cubic.argtypes = [dp, dp, C.c_size_t, C.c_double, dp, C.c_double, dp, dp]
+    lib.sh_row_linear.argtypes = [dp, dp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
+    rng = np.random.default_rng(7)
+    P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    for n in (1, 2, 3, 5, 8, 13, 1001, 15447):
+        tn = np.ascontiguousarray(rng.uniform(1e-3, 2.0, size=(4, n)))
+        tc = np.ascontiguousarray(rng.uniform(0.5, 3.0, size=(4, n)))
+        x = np.array([0.62, 0.71, 0.83, 1.0])
+        fast, scalar = np.empty(n), np.empty(n)
+        lib.sh_row_cubic(P(tn), P(tc), n, 0.0123, P(x), 1.0, P(fast), P(scalar))
+        assert np.array_equal(fast, scalar)
+        lib.sh_row_cubic(P(tn), P(tc), n, 0.0123, P(x), 0.9, P(fast), P(scalar))
+        assert np.array_equal(fast, scalar) and np.all(np.isfinite(fast))
+        lib.sh_row_linear(P(tn), P(tc), n, 0.0123, 0.83, 1.0, 1.0, P(fast), P(scalar))
+        assert np.array_equal(fast, scalar)
