@@ -640,7 +640,7 @@ def run_b200(a, rank, world, local_rank):
             "traffic": traffic,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed from %s (ncu --set full of "
                             "tools/bench_integrals.py 64: 64 cosmologies x 42 matvec sets = 74.3 GFLOP algorithmic; the "
-                            "23.7 MB weight tables stream from L2, DRAM sees them once)" % os.path.relpath(traffic_src, ROOT),
+                            "23.7 MB of weight tables that launch reads stream from L2, DRAM sees them once)" % os.path.relpath(traffic_src, ROOT),
             "peak_source": "register-resident DMMA.8x8x4 loop measured live by rtrg_bench_dmma (MEASURED_PEAKS.json has no "
                            "FP64 figure); a scalar DFMA loop (rtrg_bench_dfma) reaches %.2f; nominal 148 SM x 64 FMA/clk "
                            "x 2 x 1.965 GHz = %.1f TFLOP/s.  k_bilinear issues its FMAs as DMMA.8x8x4: the same FP64 "
