@@ -92,3 +92,19 @@ def test_v_split_changes_only_round_off(example1_full_dir):
     ref4, _, _ = run_single(example1_full_dir, v_split=4)
     res, _ = run_sharded(example1_full_dir, 2, v_split=4)
     assert np.array_equal(res[0][0][0], ref4) and np.array_equal(res[1][0][0], ref4)
+
+
+def test_fused_stage_kernel_is_bit_identical(example1_full_dir, monkeypatch):
+    """Small launches run assembly + right-hand side + next-stage combination (or the error estimate)
+    as ONE kernel (k_stage_post) built from the device functions of k_assemble / k_rhs / k_combine /
+    k_final.  Switching it off (RTRG_NO_STAGE_FUSION, read by every rtrg_run) must not change a bit,
+    sharded or not."""
+    fused, _, cnt_f = run_single(example1_full_dir)
+    res_f, _ = run_sharded(example1_full_dir, 2)
+    monkeypatch.setenv("RTRG_NO_STAGE_FUSION", "1")
+    plain, _, cnt_p = run_single(example1_full_dir)
+    res_p, _ = run_sharded(example1_full_dir, 2)
+    assert cnt_f == cnt_p
+    assert np.array_equal(fused, plain)
+    for r in range(2):
+        assert np.array_equal(res_f[r][0][0], plain) and np.array_equal(res_p[r][0][0], plain)
