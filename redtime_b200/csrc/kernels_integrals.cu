@@ -169,10 +169,9 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-template <int NWARP, int MT, int NS, int MINB>
-__global__ void __launch_bounds__(NWARP * 32, MINB)
-    k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
-               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
+template <int NWARP, int MT, int NS>
+__device__ __forceinline__ void bil_body(const IntegralTabs &tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+               double *__restrict__ Jpart, const BilLaunch &L, int rb_lo, int rb_hi, int c_lo,
                const int *__restrict__ act, const int *__restrict__ nact) {
   constexpr int R = BIL_R, VC = 8;                  // rows per row block; lags per chunk
   constexpr int IPC = NWARP * MT * 8;               // items (alpha-side lags) per CTA
@@ -372,6 +371,22 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
   }
 }
 
+template <int NWARP, int MT, int NS, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB)
+    k_bilinear(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+               double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
+               const int *__restrict__ act, const int *__restrict__ nact) {
+  bil_body<NWARP, MT, NS>(tb, cosmo, Prev, Jpart, L, rb_lo, rb_hi, c_lo, act, nact);
+}
+// the same with a register cap instead of an occupancy target (experiments: room for other kernels)
+template <int NWARP, int MT, int NS, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
+    k_bilinear_r(IntegralTabs tb, const Cosmo *__restrict__ cosmo, const double *__restrict__ Prev,
+                 double *__restrict__ Jpart, const __grid_constant__ BilLaunch L, int rb_lo, int rb_hi, int c_lo,
+                 const int *__restrict__ act, const int *__restrict__ nact) {
+  bil_body<NWARP, MT, NS>(tb, cosmo, Prev, Jpart, L, rb_lo, rb_hi, c_lo, act, nact);
+}
+
 // ---------------------------------------------------------------------------- k_jlo
 // J_{000}(P00,P00) at the padded row nloMR, needed by P_MR,4..6 (rt:1252,1267-1272)
 __global__ void __launch_bounds__(256)
@@ -469,7 +484,7 @@ struct BilVariant {
   int nwarp, mt, ns;
   int ipc() const { return nwarp * mt * 8; }  // items (alpha-side lags) per CTA
 };
-static const BilVariant kBilVariants[] = {{8, 4, 3}, {8, 2, 3}, {16, 2, 3}, {4, 4, 3}, {8, 2, 4}, {4, 2, 3}, {16, 1, 3}};
+static const BilVariant kBilVariants[] = {{8, 4, 3}, {8, 2, 3}, {16, 2, 3}, {4, 4, 3}, {8, 2, 4}, {4, 2, 3}, {16, 1, 3}, {8, 3, 3}, {8, 3, 3}, {8, 4, 3}};
 static int bil_variant_index() {
   static const int v = [] {
     const char *e = std::getenv("RTRG_BIL_VARIANT");
@@ -492,6 +507,9 @@ static auto bil_dispatch(F &&f) {
     case 4: return f(k_bilinear<8, 2, 4, 3>, kBilVariants[4]);
     case 5: return f(k_bilinear<4, 2, 3, 8>, kBilVariants[5]);
     case 6: return f(k_bilinear<16, 1, 3, 4>, kBilVariants[6]);
+    case 7: return f(k_bilinear<8, 3, 3, 2>, kBilVariants[7]);
+    case 8: return f(k_bilinear_r<8, 3, 3, 96>, kBilVariants[8]);
+    case 9: return f(k_bilinear_r<8, 4, 3, 104>, kBilVariants[9]);
     default: return f(k_bilinear<8, 4, 3, 2>, kBilVariants[0]);
   }
 }
